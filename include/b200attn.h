@@ -1,0 +1,193 @@
+/*
+ * b200attn.h -- C ABI of libb200attn.so: the paged-KV decode/attention hot path
+ * of nano-vllm (reference: linzm1007/nano-vllm-ascend) as hand-written sm_100a CUDA.
+ *
+ * Boundary contract:
+ *   - plain C, raw device pointers + sizes, no torch types;
+ *   - the caller owns every buffer (q/k/v, paged caches, tables, outputs, workspaces);
+ *   - every entry point only ENQUEUES work on `stream` (a cudaStream_t): no allocation,
+ *     no synchronisation, no host<->device copies  => CUDA-graph capturable;
+ *   - return value: 0 on success, a negative B200_ERR_* for rejected arguments, a
+ *     positive cudaError_t value if the launch itself failed;
+ *   - KV caches are written in place (same as the reference's
+ *     torch_npu._npu_reshape_and_cache / scatter_update_, layers/attention.py:25-35).
+ *
+ * The reference has no native FFI of its own: its "FFI" for this path is the vendor op
+ * table reached through torch dispatch (torch_npu.* / torchair / flash_attn / triton).
+ * Each entry point below cites the reference call site(s) it replaces; paths are
+ * relative to the reference checkout, line numbers as of commit ec1ffe9a.
+ *
+ * dtype: element type of q/k/v/caches/activations: B200_DTYPE_BF16 or B200_DTYPE_F16.
+ * All index tensors are int32 unless stated (positions: int64, as the reference's
+ * model_runner.py:274-275 builds them).
+ */
+#ifndef B200ATTN_H_
+#define B200ATTN_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ATTN_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+enum {
+  B200_DTYPE_BF16 = 0,
+  B200_DTYPE_F16 = 1,
+};
+
+enum {
+  B200_OK = 0,
+  B200_ERR_NULL_POINTER = -1,
+  B200_ERR_BAD_SHAPE = -2,       /* zero/negative dims, H % Hkv != 0, ... */
+  B200_ERR_UNSUPPORTED = -3,     /* head_dim not in {64,128}, group size > 8, Hkv not 1/2/4/8k ... */
+  B200_ERR_MISALIGNED = -4,      /* pointer / stride not 16-byte aligned */
+  B200_ERR_WORKSPACE = -5,       /* workspace too small */
+  B200_ERR_DRIVER = -6,          /* cuTensorMapEncodeTiled unavailable / failed */
+  B200_ERR_BAD_DTYPE = -7,
+};
+
+/* Version of the loaded library (== B200ATTN_VERSION it was built with). */
+int b200_version(void);
+/* Human-readable text for a return code of any function below. Never NULL. */
+const char* b200_error_string(int code);
+/* Number of kernels this library has enqueued since load / since the last reset
+ * (host-side counter; lets bench.py report `gpu_launches`). */
+int64_t b200_launch_count(void);
+void b200_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * K1  reshape_and_cache, flat slots.
+ * Replaces: torch_npu._npu_reshape_and_cache        layers/attention.py:25-30
+ *           triton store_kvcache_kernel              layers/attention_ori.py:10-40
+ *           store_kvcache (torch native, the oracle) layers/attention_torch_native.py:13-51
+ * key/value: [num_tokens, num_kv_heads, head_dim], token stride in ELEMENTS
+ *            (key_stride/value_stride; heads and head_dim contiguous).
+ * k_cache/v_cache: [num_blocks, block_size, num_kv_heads*head_dim] contiguous.
+ * slot_mapping[i] = block*block_size + offset; slot == -1 or out of range => skipped
+ * (attention_ori.py:23, attention_torch_native.py:27-35).
+ * ------------------------------------------------------------------------------- */
+int b200_reshape_and_cache(const void* key, const void* value, void* k_cache, void* v_cache,
+                           const int32_t* slot_mapping, int32_t num_tokens,
+                           int32_t num_kv_heads, int32_t head_dim, int64_t key_stride,
+                           int64_t value_stride, int32_t num_blocks, int32_t block_size,
+                           int32_t dtype, b200_stream_t stream);
+
+/* K2  reshape_and_cache, 2-D slots [num_tokens, 2] = (block_id, offset), the decode form.
+ * Replaces: torch_npu.scatter_update_ x2             layers/attention.py:32-35
+ *           (index built at engine/model_runner.py:301,315,353). */
+int b200_reshape_and_cache_2d(const void* key, const void* value, void* k_cache,
+                              void* v_cache, const int32_t* slot_pairs, int32_t num_tokens,
+                              int32_t num_kv_heads, int32_t head_dim, int64_t key_stride,
+                              int64_t value_stride, int32_t num_blocks, int32_t block_size,
+                              int32_t dtype, b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * K6  paged decode attention (one query token per sequence).
+ * Replaces: npu_fused_infer_attention_score_v2 BNSD + block_table  layers/attention.py:64-76
+ *           tng.ops.npu_fused_infer_attention_score (graph mode)   layers/attention.py:80-92
+ *           flash_attn_with_kvcache                                layers/attention_ori.py:72-74
+ *           Attention._decode_attn (oracle)                layers/attention_torch_native.py:147-196
+ * q:   [batch, num_heads, head_dim], token stride q_stride (elements).
+ * out: [batch, num_heads*head_dim],  token stride out_stride (elements).
+ * k_cache/v_cache: [num_blocks, block_size, num_kv_heads*head_dim] contiguous.
+ * block_tables: [batch, block_table_stride] int32, -1 padded; context_lens: [batch] int32
+ * (tokens to attend INCLUDING the one just stored). context_len == 0 => that row of
+ * `out` is written as zeros and nothing else is touched (padded graph rows,
+ * engine/model_runner.py:303-311).
+ * workspace: >= b200_paged_decode_attn_workspace_size(...) bytes, 16-byte aligned.
+ * num_ctas: 0 = auto (one persistent CTA per SM), otherwise the persistent grid size.
+ * ------------------------------------------------------------------------------- */
+size_t b200_paged_decode_attn_workspace_size(int32_t batch, int32_t num_heads,
+                                             int32_t num_kv_heads, int32_t head_dim);
+int b200_paged_decode_attn(void* out, const void* q, const void* k_cache, const void* v_cache,
+                           const int32_t* block_tables, const int32_t* context_lens,
+                           int32_t batch, int32_t num_heads, int32_t num_kv_heads,
+                           int32_t head_dim, int64_t q_stride, int64_t out_stride,
+                           int32_t num_blocks, int32_t block_size,
+                           int32_t block_table_stride, float scale, void* workspace,
+                           size_t workspace_bytes, int32_t num_ctas, int32_t dtype,
+                           b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * K4/K5  varlen causal prefill flash-attention.
+ * Replaces: npu_fused_infer_attention_score_v2 TND, sparse_mode=3  layers/attention.py:49-59
+ *           flash_attn_varlen_func(causal=True[, block_table])     layers/attention_ori.py:63-70
+ *           Attention._prefill_attn (oracle)               layers/attention_torch_native.py:103-145
+ * q: [total_q, num_heads, head_dim] (token stride q_stride), out: [total_q, num_heads*head_dim].
+ * Contiguous K/V mode (block_tables == NULL): k/v: [total_k, num_kv_heads, head_dim] with
+ *   token strides k_stride/v_stride; cu_seqlens_k indexes them.
+ * Paged K/V mode (block_tables != NULL, the prefix-cache-hit form of attention_ori.py:65-66):
+ *   k/v are the paged caches [num_blocks, block_size, num_kv_heads*head_dim]; sequence i's
+ *   keys are its first (cu_seqlens_k[i+1]-cu_seqlens_k[i]) cached tokens via block_tables[i].
+ * Causal mask is bottom-right aligned (query row r of a sequence with Lq queries and Lk keys
+ * sees keys 0 .. r + Lk - Lq), == NPU sparse_mode=3 and flash-attn causal; identical to the
+ * oracle's top-left mask whenever Lq == Lk, which is the only case the reference runner
+ * produces (engine/model_runner.py:252-256).
+ * ------------------------------------------------------------------------------- */
+int b200_prefill_varlen_attn(void* out, const void* q, const void* k, const void* v,
+                             const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                             int32_t num_seqs, int32_t max_seqlen_q, int32_t max_seqlen_k,
+                             int32_t num_heads, int32_t num_kv_heads, int32_t head_dim,
+                             int64_t q_stride, int64_t k_stride, int64_t v_stride,
+                             int64_t out_stride, const int32_t* block_tables,
+                             int32_t block_table_stride, int32_t num_blocks,
+                             int32_t block_size, float scale, int32_t dtype,
+                             b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * K8  fused qkv epilogue: split -> per-head RMSNorm(q,k) -> NeoX RoPE(q,k) -> KV scatter.
+ * Replaces the op chain models/qwen3.py:79-88 (q_norm/k_norm: layers/layernorm.py:16-25;
+ * rotary: layers/rotary_embedding.py:6-14,37-47; scatter: K1/K2 above).
+ * qkv: [num_tokens, (H + 2*Hkv)*D] contiguous rows (row stride qkv_stride elements);
+ *      q and k are normalised + rotated IN PLACE (v untouched), so q = qkv[:, :H*D] etc.
+ *      stay valid views for the attention kernels.
+ * positions: [num_tokens] int64. cos_sin_cache: [max_position, D] fp32 (cos | sin halves),
+ *      rotary_embedding.py:26-35.
+ * q_norm_weight/k_norm_weight: [D] in dtype, or NULL for models without QK-norm
+ *      (qkv_bias models, models/qwen3.py:70-72; Llama).
+ * k_cache/v_cache may be NULL (no cache bound yet: warm-up, attention_ori.py:62).
+ * slots: flat [num_tokens] when slot_is_2d == 0, else [num_tokens,2] (block, offset).
+ * ------------------------------------------------------------------------------- */
+int b200_qknorm_rope_cache(void* qkv, const int64_t* positions, const float* cos_sin_cache,
+                           const void* q_norm_weight, const void* k_norm_weight, float eps,
+                           void* k_cache, void* v_cache, const int32_t* slots,
+                           int32_t slot_is_2d, int32_t num_tokens, int32_t num_heads,
+                           int32_t num_kv_heads, int32_t head_dim, int64_t qkv_stride,
+                           int32_t max_position, int32_t num_blocks, int32_t block_size,
+                           int32_t dtype, b200_stream_t stream);
+
+/* F1  RMSNorm: out = cast(x_fp32 * rsqrt(mean(x^2)+eps)) * weight   layers/layernorm.py:16-25
+ * x, out: [rows, hidden] contiguous (out may alias x). */
+int b200_rmsnorm(void* out, const void* x, const void* weight, float eps, int32_t rows,
+                 int32_t hidden, int32_t dtype, b200_stream_t stream);
+
+/* F1' fused residual-add + RMSNorm                                   layers/layernorm.py:27-38
+ * residual <- cast(x + residual); x <- RMSNorm(fp32(x + residual)) * weight. Both in place. */
+int b200_add_rmsnorm(void* x, void* residual, const void* weight, float eps, int32_t rows,
+                     int32_t hidden, int32_t dtype, b200_stream_t stream);
+
+/* F3  SiluAndMul: out[r, i] = silu(x[r, i]) * x[r, inter + i]         layers/activation.py:11-13
+ * x: [rows, 2*inter] contiguous, out: [rows, inter] contiguous. */
+int b200_silu_and_mul(void* out, const void* x, int32_t rows, int32_t inter, int32_t dtype,
+                      b200_stream_t stream);
+
+/* f2 (SURVEY 8f "next"): greedy/temperature sampling tail without the fp32 logits
+ * round trip. Replaces layers/sampler.py:9-17 for the greedy parity path (argmax) and
+ * for temperature sampling via the Gumbel-max trick with a counter-based RNG.
+ * logits: [rows, vocab] in dtype (row stride logits_stride elements);
+ * temperatures: [rows] fp32 or NULL (=> argmax). out_tokens: [rows] int64.
+ * Gumbel sampling draws the same distribution as softmax+multinomial but not the same
+ * random stream as torch.multinomial; only the argmax form is bit-comparable. */
+int b200_sample(int64_t* out_tokens, const void* logits, const float* temperatures,
+                int32_t rows, int32_t vocab, int64_t logits_stride, uint64_t seed,
+                uint64_t step, int32_t dtype, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ATTN_H_ */

@@ -1,0 +1,236 @@
+"""Tensor-level wrappers over the C ABI: torch owns memory and streams, CUDA does the work.
+
+Each function validates what the C side cannot know (device, dtype, contiguity of the inner
+dimensions), then passes raw pointers + the current stream. All of them enqueue only; they
+are safe inside CUDA-graph capture.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _C
+
+_DT = {torch.bfloat16: _C.BF16, torch.float16: _C.F16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"b200attn kernels take bf16/fp16 tensors, got {t.dtype}") from None
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "b200attn: the hot path runs on CUDA only (got a CPU tensor); there is no "
+                "CPU fallback -- use oracle/ for CPU reference results")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _cache_dims(cache: torch.Tensor, row_elems: int) -> tuple[int, int]:
+    """(num_blocks, block_size) of a cache given as [nb, bs, Hkv*D] or [nb, bs, Hkv, D]."""
+    if cache.dim() not in (3, 4) or not cache.is_contiguous():
+        raise ValueError("KV cache must be a contiguous [nb, bs, Hkv*D] (or [nb, bs, Hkv, D]) tensor")
+    if cache[0, 0].numel() != row_elems:
+        raise ValueError(f"KV cache row has {cache[0, 0].numel()} elements, expected {row_elems}")
+    return cache.shape[0], cache.shape[1]
+
+
+def launch_count() -> int:
+    return _C.load().b200_launch_count()
+
+
+def reset_launch_count() -> None:
+    _C.load().b200_reset_launch_count()
+
+
+def reshape_and_cache(key, value, k_cache, v_cache, slot_mapping):
+    """K1/K2. key/value [T, Hkv, D] (token-strided views allowed), slot_mapping [T] flat or
+    [T, 2] (block, offset); int32."""
+    _need_cuda(key, value, k_cache, v_cache, slot_mapping)
+    T, Hkv, D = key.shape
+    if value.shape != key.shape:
+        raise ValueError("key/value shape mismatch")
+    if key.stride(2) != 1 or key.stride(1) != D or value.stride(2) != 1 or value.stride(1) != D:
+        raise ValueError("key/value must be contiguous in (heads, head_dim)")
+    if slot_mapping.dtype != torch.int32 or not slot_mapping.is_contiguous():
+        raise TypeError("slot_mapping must be a contiguous int32 tensor")
+    nb, bs = _cache_dims(k_cache, Hkv * D)
+    lib = _C.load()
+    two_d = slot_mapping.dim() == 2
+    if slot_mapping.shape[0] != T or (two_d and slot_mapping.shape[1] != 2):
+        raise ValueError(f"slot_mapping shape {tuple(slot_mapping.shape)} does not match {T} tokens")
+    fn = lib.b200_reshape_and_cache_2d if two_d else lib.b200_reshape_and_cache
+    _C.check(fn(key.data_ptr(), value.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+                slot_mapping.data_ptr(), T, Hkv, D, key.stride(0) if T > 1 else Hkv * D,
+                value.stride(0) if T > 1 else Hkv * D, nb, bs, _dt(key), _stream()),
+             "b200_reshape_and_cache")
+
+
+_decode_ws: dict = {}
+
+
+def decode_workspace(batch, num_heads, num_kv_heads, head_dim, device) -> torch.Tensor:
+    need = _C.load().b200_paged_decode_attn_workspace_size(batch, num_heads, num_kv_heads, head_dim)
+    if need == 0:
+        raise _C.B200Error("b200_paged_decode_attn: unsupported head configuration "
+                           f"(H={num_heads}, Hkv={num_kv_heads}, D={head_dim})")
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _decode_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _decode_ws[key] = ws
+    return ws
+
+
+def paged_decode_attn(q, k_cache, v_cache, block_tables, context_lens, scale, num_kv_heads,
+                      out=None, workspace=None, num_ctas=0):
+    """K6. q [B, H, D] (token-strided view allowed) -> out [B, H*D]."""
+    _need_cuda(q, k_cache, v_cache, block_tables, context_lens)
+    B, H, D = q.shape
+    if q.stride(2) != 1 or q.stride(1) != D:
+        raise ValueError("q must be contiguous in (heads, head_dim)")
+    if block_tables.dtype != torch.int32 or context_lens.dtype != torch.int32:
+        raise TypeError("block_tables/context_lens must be int32")
+    if block_tables.dim() != 2 or block_tables.stride(1) != 1 or not context_lens.is_contiguous():
+        raise ValueError("block_tables must be [B, max_blocks] row-major, context_lens contiguous")
+    nb, bs = _cache_dims(k_cache, num_kv_heads * D)
+    if out is None:
+        out = torch.empty(B, H * D, dtype=q.dtype, device=q.device)
+    if workspace is None:
+        workspace = decode_workspace(B, H, num_kv_heads, D, q.device)
+    _C.check(_C.load().b200_paged_decode_attn(
+        out.data_ptr(), q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+        block_tables.data_ptr(), context_lens.data_ptr(), B, H, num_kv_heads, D,
+        q.stride(0) if B > 1 else H * D, out.stride(0) if B > 1 else H * D, nb, bs,
+        block_tables.stride(0), float(scale), workspace.data_ptr(), workspace.numel(),
+        int(num_ctas), _dt(q), _stream()), "b200_paged_decode_attn")
+    return out
+
+
+def prefill_varlen_attn(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, scale,
+                        num_kv_heads, block_tables=None, out=None):
+    """K4/K5. q [Tq, H, D]; packed mode: k/v [Tk, Hkv, D]; paged mode (block_tables given):
+    k/v are the caches [nb, bs, Hkv*D]. Returns out [Tq, H*D]."""
+    _need_cuda(q, k, v, cu_seqlens_q, cu_seqlens_k, block_tables)
+    Tq, H, D = q.shape
+    if q.stride(2) != 1 or q.stride(1) != D:
+        raise ValueError("q must be contiguous in (heads, head_dim)")
+    if cu_seqlens_q.dtype != torch.int32 or cu_seqlens_k.dtype != torch.int32:
+        raise TypeError("cu_seqlens must be int32")
+    num_seqs = cu_seqlens_q.numel() - 1
+    if out is None:
+        out = torch.empty(Tq, H * D, dtype=q.dtype, device=q.device)
+    if block_tables is not None:
+        if block_tables.dtype != torch.int32 or block_tables.stride(1) != 1:
+            raise TypeError("block_tables must be row-major int32")
+        nb, bs = _cache_dims(k, num_kv_heads * D)
+        ks = vs = num_kv_heads * D
+        bt_ptr, bt_stride = block_tables.data_ptr(), block_tables.stride(0)
+    else:
+        if k.stride(2) != 1 or k.stride(1) != D or v.stride(2) != 1 or v.stride(1) != D:
+            raise ValueError("k/v must be contiguous in (heads, head_dim)")
+        nb = bs = 0
+        ks = k.stride(0) if k.shape[0] > 1 else num_kv_heads * D
+        vs = v.stride(0) if v.shape[0] > 1 else num_kv_heads * D
+        bt_ptr, bt_stride = None, 0
+    _C.check(_C.load().b200_prefill_varlen_attn(
+        out.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), cu_seqlens_q.data_ptr(),
+        cu_seqlens_k.data_ptr(), num_seqs, int(max_seqlen_q), int(max_seqlen_k), H, num_kv_heads,
+        D, q.stride(0) if Tq > 1 else H * D, ks, vs, out.stride(0) if Tq > 1 else H * D, bt_ptr,
+        bt_stride, nb, bs, float(scale), _dt(q), _stream()), "b200_prefill_varlen_attn")
+    return out
+
+
+def qknorm_rope_cache(qkv, positions, cos_sin_cache, q_norm_weight, k_norm_weight, eps,
+                      k_cache, v_cache, slots, num_heads, num_kv_heads, head_dim):
+    """K8, in place on qkv [T, (H+2Hkv)*D]. k_cache/v_cache/slots may be None (no cache bound)."""
+    _need_cuda(qkv, positions, cos_sin_cache, q_norm_weight, k_norm_weight, k_cache, v_cache, slots)
+    T = qkv.shape[0]
+    if qkv.dim() != 2 or qkv.stride(1) != 1:
+        raise ValueError("qkv must be [T, (H+2Hkv)*D] with unit inner stride")
+    if positions.dtype != torch.int64 or not positions.is_contiguous():
+        raise TypeError("positions must be contiguous int64")
+    if cos_sin_cache.dtype != torch.float32 or not cos_sin_cache.is_contiguous():
+        raise TypeError("cos_sin_cache must be contiguous fp32")
+    if cos_sin_cache.shape[-1] != head_dim:
+        raise ValueError("cos_sin_cache last dim must equal head_dim")
+    have_cache = k_cache is not None and k_cache.numel() > 0
+    nb = bs = 0
+    if have_cache:
+        nb, bs = _cache_dims(k_cache, num_kv_heads * head_dim)
+        if slots.dtype != torch.int32 or not slots.is_contiguous():
+            raise TypeError("slots must be contiguous int32")
+    _C.check(_C.load().b200_qknorm_rope_cache(
+        qkv.data_ptr(), positions.data_ptr(), cos_sin_cache.data_ptr(), _ptr(q_norm_weight),
+        _ptr(k_norm_weight), float(eps), k_cache.data_ptr() if have_cache else None,
+        v_cache.data_ptr() if have_cache else None, slots.data_ptr() if have_cache else None,
+        1 if (have_cache and slots.dim() == 2) else 0, T, num_heads, num_kv_heads, head_dim,
+        qkv.stride(0) if T > 1 else qkv.shape[1], cos_sin_cache.shape[0], nb, bs, _dt(qkv),
+        _stream()), "b200_qknorm_rope_cache")
+    return qkv
+
+
+def rmsnorm(x, weight, eps, out=None):
+    _need_cuda(x, weight)
+    if not x.is_contiguous():
+        raise ValueError("rmsnorm input must be contiguous")
+    hidden = x.shape[-1]
+    rows = x.numel() // hidden if hidden else 0
+    if out is None:
+        out = torch.empty_like(x)
+    _C.check(_C.load().b200_rmsnorm(out.data_ptr(), x.data_ptr(), weight.data_ptr(), float(eps),
+                                    rows, hidden, _dt(x), _stream()), "b200_rmsnorm")
+    return out
+
+
+def add_rmsnorm_(x, residual, weight, eps):
+    """In place: residual <- x + residual; x <- RMSNorm(x + residual) * weight."""
+    _need_cuda(x, residual, weight)
+    if not (x.is_contiguous() and residual.is_contiguous()):
+        raise ValueError("add_rmsnorm tensors must be contiguous")
+    hidden = x.shape[-1]
+    rows = x.numel() // hidden if hidden else 0
+    _C.check(_C.load().b200_add_rmsnorm(x.data_ptr(), residual.data_ptr(), weight.data_ptr(),
+                                        float(eps), rows, hidden, _dt(x), _stream()),
+             "b200_add_rmsnorm")
+    return x, residual
+
+
+def silu_and_mul(x, out=None):
+    _need_cuda(x)
+    if not x.is_contiguous():
+        raise ValueError("silu_and_mul input must be contiguous")
+    inter = x.shape[-1] // 2
+    rows = x.numel() // (2 * inter) if inter else 0
+    if out is None:
+        out = torch.empty(*x.shape[:-1], inter, dtype=x.dtype, device=x.device)
+    _C.check(_C.load().b200_silu_and_mul(out.data_ptr(), x.data_ptr(), rows, inter, _dt(x),
+                                         _stream()), "b200_silu_and_mul")
+    return out
+
+
+def sample(logits, temperatures=None, seed=0, step=0, out=None):
+    """argmax (temperatures=None) or Gumbel-max sampling over [rows, vocab] bf16/fp16 logits."""
+    _need_cuda(logits, temperatures)
+    rows, vocab = logits.shape
+    if logits.stride(1) != 1:
+        raise ValueError("logits must have unit inner stride")
+    if temperatures is not None and (temperatures.dtype != torch.float32 or
+                                     not temperatures.is_contiguous()):
+        raise TypeError("temperatures must be contiguous fp32")
+    if out is None:
+        out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    _C.check(_C.load().b200_sample(out.data_ptr(), logits.data_ptr(), _ptr(temperatures), rows,
+                                   vocab, logits.stride(0) if rows > 1 else vocab, int(seed),
+                                   int(step), _dt(logits), _stream()), "b200_sample")
+    return out

@@ -1,0 +1,245 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference code on CPU.
+
+Run in the build container only (needs /root/reference):  python -m oracle.gen_golden
+The reference package cannot be imported whole (torch_npu/torchair are absent), so a
+namespace stub is registered and only its CPU-capable modules are imported: the torch-native
+attention (layers/attention_torch_native.py), the eager layers, and models/qwen3.py with the
+NPU attention module replaced by a constructor-adapting shim around the torch-native class
+(SURVEY.md 8c). The runner metadata (prepare_prefill / prepare_decode) is restated in
+oracle/model_ref.py because engine/model_runner.py is NPU-bound.
+
+Outputs are inputs + reference outputs for seeded cases; tests/test_oracle_golden.py replays
+them through oracle/*.py (bit-exact on CPU) and the -m gpu tests replay them on the B200.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import types
+
+import torch
+
+REF = os.environ.get("B200_REFERENCE_DIR", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    pkg = types.ModuleType("nanovllm")
+    pkg.__path__ = [os.path.join(REF, "nanovllm")]
+    sys.modules["nanovllm"] = pkg
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29713", world_size=1, rank=0)
+    from nanovllm.layers import attention_torch_native as native
+
+    class ShimAttention(native.Attention):
+        """models/*.py construct Attention(num_heads, head_dim, scaling, num_kv_heads);
+        the torch-native class takes (num_heads, head_dim, num_kv_heads, block_size)."""
+        block_size = 16
+
+        def __init__(self, num_heads, head_dim, scaling, num_kv_heads):
+            super().__init__(num_heads, head_dim, num_kv_heads, ShimAttention.block_size)
+
+    shim = types.ModuleType("nanovllm.layers.attention")
+    shim.Attention = ShimAttention
+    sys.modules["nanovllm.layers.attention"] = shim
+    return native, ShimAttention
+
+
+def set_ctx(meta):
+    from nanovllm.utils.context import set_context
+    set_context(meta.is_prefill, cu_seqlens_q=meta.cu_seqlens_q, cu_seqlens_k=meta.cu_seqlens_k,
+                max_seqlen_q=0, max_seqlen_k=0, slot_mapping=meta.slot_mapping,
+                context_lens=meta.context_lens, block_tables=meta.block_tables,
+                is_enforce_eager=True, real_bs=-1, block_size=16)
+
+
+def gen_kernels(native):
+    from oracle import layers_ref  # only for the rope table constructor arguments
+    g = torch.Generator().manual_seed(1234)
+    bf = torch.bfloat16
+    out = {}
+
+    # ---- KV scatter (attention_torch_native.store_kvcache)
+    N, G, D, nb, bs = 40, 2, 64, 6, 16
+    key = torch.randn(N, G, D, generator=g).to(bf)
+    val = torch.randn(N, G, D, generator=g).to(bf)
+    kc = torch.randn(nb, bs, G, D, generator=g).to(bf)
+    vc = torch.randn(nb, bs, G, D, generator=g).to(bf)
+    slots = torch.randperm(nb * bs, generator=g)[:N].to(torch.int32)
+    slots[3] = -1
+    slots[17] = -1
+    slots[29] = nb * bs + 5          # out of range -> dropped
+    kc_out, vc_out = kc.clone(), vc.clone()
+    native.store_kvcache(key, val, kc_out, vc_out, slots, bs)
+    out["kv_scatter"] = dict(key=key, value=val, k_cache=kc, v_cache=vc, slot_mapping=slots,
+                             block_size=bs, k_cache_out=kc_out, v_cache_out=vc_out)
+
+    # ---- decode + prefill attention (Attention._decode_attn / _prefill_attn)
+    for tag, (H, G, D) in {"d64": (4, 2, 64), "d128": (4, 2, 128)}.items():
+        nb, bs = 14, 16
+        attn = native.Attention(H, D, G, bs)
+        attn.k_cache = (0.5 * torch.randn(nb, bs, G, D, generator=g)).to(bf)
+        attn.v_cache = torch.randn(nb, bs, G, D, generator=g).to(bf)
+        ctx = torch.tensor([1, 16, 17, 40, 33, 64], dtype=torch.int32)
+        perm = torch.randperm(nb, generator=g).tolist()
+        tables, p = [], 0
+        for n in ctx.tolist():
+            k = (n + bs - 1) // bs
+            tables.append(perm[p:p + k] if p + k <= nb else perm[:k])
+            p = (p + k) % nb
+        width = max(len(t) for t in tables)
+        bt = torch.tensor([t + [-1] * (width - len(t)) for t in tables], dtype=torch.int32)
+        q = torch.randn(len(ctx), H, D, generator=g).to(bf)
+        o = attn._decode_attn(q, ctx, bt, torch.device("cpu")).reshape(len(ctx), -1)
+        out[f"decode_{tag}"] = dict(q=q, k_cache=attn.k_cache, v_cache=attn.v_cache,
+                                    context_lens=ctx, block_tables=bt, num_kv_heads=G,
+                                    head_dim=D, out=o)
+        lens = [5, 16, 33, 70]
+        cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+        T = int(cu[-1])
+        q = torch.randn(T, H, D, generator=g).to(bf)
+        k = (0.5 * torch.randn(T, G, D, generator=g)).to(bf)
+        v = torch.randn(T, G, D, generator=g).to(bf)
+        o = attn._prefill_attn(q, k, v, cu, cu, torch.device("cpu")).reshape(T, -1)
+        out[f"prefill_{tag}"] = dict(q=q, k=k, v=v, cu_seqlens=cu, num_kv_heads=G, head_dim=D,
+                                     out=o)
+
+    # ---- eager layers
+    from nanovllm.layers.layernorm import RMSNorm
+    from nanovllm.layers.rotary_embedding import RotaryEmbedding
+    from nanovllm.layers.activation import SiluAndMul
+    for hidden in (128, 1024):
+        norm = RMSNorm(hidden, 1e-6)
+        norm.weight.data = (1 + 0.1 * torch.randn(hidden, generator=g)).to(bf)
+        x = torch.randn(7, hidden, generator=g).to(bf)
+        r = torch.randn(7, hidden, generator=g).to(bf)
+        y = norm(x.clone())
+        y2, r2 = norm(x.clone(), r.clone())
+        out[f"rmsnorm_{hidden}"] = dict(x=x, residual=r, weight=norm.weight.data.clone(), eps=1e-6,
+                                        out=y, add_out=y2, add_residual=r2)
+    for D in (64, 128):
+        rope = RotaryEmbedding(D, D, 256, 1000000.0)
+        pos = torch.tensor([0, 1, 2, 17, 100, 255], dtype=torch.int64)
+        q = torch.randn(6, 4, D, generator=g).to(bf)
+        k = torch.randn(6, 2, D, generator=g).to(bf)
+        qo, ko = rope(pos, q, k)
+        out[f"rope_{D}"] = dict(positions=pos, q=q, k=k, base=1000000.0, max_position=256,
+                                q_out=qo, k_out=ko, cos_sin_cache=rope.cos_sin_cache.clone())
+    x = (3 * torch.randn(5, 2 * 96, generator=g)).to(bf)
+    out["silu_and_mul"] = dict(x=x, out=SiluAndMul()(x))
+    return out
+
+
+def build_reference_model(cfg, weights):
+    """Reference Qwen3ForCausalLM (models/qwen3.py) on CPU in cfg.dtype with `weights`."""
+    from transformers import Qwen3Config
+    from nanovllm.models.qwen3 import Qwen3ForCausalLM
+    from nanovllm.layers.rotary_embedding import get_rope
+    get_rope.cache_clear()
+    hf = Qwen3Config(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
+                     num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads,
+                     num_key_value_heads=cfg.num_kv_heads, head_dim=cfg.head_dim,
+                     intermediate_size=cfg.intermediate_size, rms_norm_eps=cfg.rms_eps,
+                     max_position_embeddings=cfg.max_position, tie_word_embeddings=True,
+                     attention_bias=False, hidden_act="silu")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(cfg.dtype)
+    try:
+        model = Qwen3ForCausalLM(hf)
+    finally:
+        torch.set_default_dtype(old)
+    params = dict(model.named_parameters())
+    for name, w in weights.items():
+        params[name].data.copy_(w)
+    model.lm_head.weight.data = model.model.embed_tokens.weight.data
+    return model.eval()
+
+
+def reference_greedy(model, cfg, prompts, max_tokens, bs):
+    """Drive the reference model with restated runner metadata; argmax sampling."""
+    from oracle import model_ref as M
+    from nanovllm.utils.context import reset_context
+    B = len(prompts)
+    need = [(len(p) + max_tokens + bs - 1) // bs for p in prompts]
+    nb = sum(need) + 1
+    tables, nxt = [], 0
+    for n in need:
+        tables.append(list(range(nxt, nxt + n)))
+        nxt += n
+    kv = torch.zeros(2, cfg.num_layers, nb, bs, cfg.num_kv_heads, cfg.head_dim, dtype=cfg.dtype)
+    lid = 0
+    for mod in model.modules():
+        if hasattr(mod, "k_cache") and hasattr(mod, "v_cache"):
+            mod.k_cache, mod.v_cache = kv[0, lid], kv[1, lid]
+            lid += 1
+    seqs = [list(p) for p in prompts]
+    toks, logs = [[] for _ in range(B)], []
+    with torch.inference_mode():
+        lens = [len(s) for s in seqs]
+        pos, meta = M.prefill_meta(lens, [t[:(n + bs - 1) // bs] for t, n in zip(tables, lens)], bs)
+        ids = torch.tensor([t for s in seqs for t in s], dtype=torch.int64)
+        set_ctx(meta)
+        logits = model.compute_logits(model(ids, pos))
+        for step in range(max_tokens):
+            nxt_tok = logits.float().argmax(-1).tolist()
+            logs.append(logits.float().clone())
+            for i, t in enumerate(nxt_tok):
+                seqs[i].append(t)
+                toks[i].append(t)
+            if step == max_tokens - 1:
+                break
+            lens = [len(s) for s in seqs]
+            pos, meta = M.decode_meta(lens, [t[:(n + bs - 1) // bs] for t, n in zip(tables, lens)], bs)
+            ids = torch.tensor([s[-1] for s in seqs], dtype=torch.int64)
+            set_ctx(meta)
+            logits = model.compute_logits(model(ids, pos))
+        reset_context()
+    return toks, logs
+
+
+def gen_models():
+    from oracle import model_ref as M
+    out = {}
+    # tiny Qwen3-shaped model: full logits kept
+    cfg = M.ModelCfg()
+    w = M.seeded_weights(cfg, seed=7, norm_jitter=0.1)
+    model = build_reference_model(cfg, w)
+    rnd = random.Random(0)
+    prompts = [[rnd.randint(0, cfg.vocab_size - 1) for _ in range(n)] for n in (20, 5, 33)]
+    toks, logs = reference_greedy(model, cfg, prompts, 10, 16)
+    out["tiny_qwen3"] = dict(seed=7, norm_jitter=0.1, prompts=prompts, max_tokens=10,
+                             block_size=16, tokens=toks, logits=torch.stack(logs))
+    # BASELINE config 1: full-size random-init Qwen3-0.6B, 1 prompt, block 16, 32 tokens
+    cfg = M.ModelCfg.qwen3_0_6b()
+    w = M.seeded_weights(cfg, seed=0)
+    model = build_reference_model(cfg, w)
+    rnd = random.Random(0)
+    prompts = [[rnd.randint(0, 10000) for _ in range(24)]]
+    toks, logs = reference_greedy(model, cfg, prompts, 32, 16)
+    lg = torch.stack(logs)[:, 0]                      # [32, vocab]
+    top = lg.topk(8, dim=-1)
+    out["qwen3_0_6b_config1"] = dict(seed=0, norm_jitter=0.0, prompts=prompts, max_tokens=32,
+                                     block_size=16, tokens=toks, top_values=top.values,
+                                     top_indices=top.indices,
+                                     logit_mean=lg.mean(-1), logit_std=lg.std(-1))
+    return out
+
+
+def main():
+    torch.manual_seed(0)
+    native, _ = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    k = gen_kernels(native)
+    torch.save(k, os.path.join(OUT, "kernels.pt"))
+    m = gen_models()
+    torch.save(m, os.path.join(OUT, "models.pt"))
+    for name in ("kernels.pt", "models.pt"):
+        print(name, os.path.getsize(os.path.join(OUT, name)), "bytes")
+    print("tiny tokens", m["tiny_qwen3"]["tokens"])
+    print("0.6B tokens", m["qwen3_0_6b_config1"]["tokens"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""Pin the oracle: every oracle function must reproduce, bit for bit on CPU, what the
+reference's own code produced for the same inputs (tests/golden/*.pt, made by
+oracle/gen_golden.py from the unmodified reference)."""
+import torch
+
+from oracle import attention_ref as A
+from oracle import layers_ref as L
+from oracle import model_ref as M
+
+
+def test_kv_scatter_matches_reference(golden_kernels):
+    g = golden_kernels["kv_scatter"]
+    kc, vc = g["k_cache"].clone(), g["v_cache"].clone()
+    A.store_kvcache(g["key"], g["value"], kc, vc, g["slot_mapping"], g["block_size"])
+    assert torch.equal(kc, g["k_cache_out"]) and torch.equal(vc, g["v_cache_out"])
+    # dropped slots really left the cache untouched
+    assert not torch.equal(kc, g["k_cache"])
+
+
+def test_decode_attention_matches_reference(golden_kernels):
+    for tag in ("d64", "d128"):
+        g = golden_kernels[f"decode_{tag}"]
+        o = A.decode_attention(g["q"], g["k_cache"], g["v_cache"], g["context_lens"],
+                               g["block_tables"], g["num_kv_heads"], g["head_dim"])
+        assert o.dtype == torch.bfloat16 and torch.equal(o, g["out"])
+        # the fp32 evaluation of the same function stays within bf16 noise of the reference
+        e = A.decode_attention(g["q"], g["k_cache"], g["v_cache"], g["context_lens"],
+                               g["block_tables"], g["num_kv_heads"], g["head_dim"], mode="exact",
+                               scale=g["head_dim"] ** -0.5)
+        assert (e - g["out"].float()).abs().max() < 6e-2
+
+
+def test_prefill_attention_matches_reference(golden_kernels):
+    for tag in ("d64", "d128"):
+        g = golden_kernels[f"prefill_{tag}"]
+        o = A.prefill_attention(g["q"], g["k"], g["v"], g["cu_seqlens"], g["cu_seqlens"],
+                                g["num_kv_heads"], g["head_dim"])
+        assert torch.equal(o, g["out"])
+        # Lq == Lk: both causal alignments are the same function
+        o2 = A.prefill_attention(g["q"], g["k"], g["v"], g["cu_seqlens"], g["cu_seqlens"],
+                                 g["num_kv_heads"], g["head_dim"], causal_align="bottom_right")
+        assert torch.equal(o2, g["out"])
+
+
+def test_layers_match_reference(golden_kernels):
+    for hidden in (128, 1024):
+        g = golden_kernels[f"rmsnorm_{hidden}"]
+        assert torch.equal(L.rmsnorm(g["x"], g["weight"], g["eps"]), g["out"])
+        y, r = L.add_rmsnorm(g["x"], g["residual"], g["weight"], g["eps"])
+        assert torch.equal(y, g["add_out"]) and torch.equal(r, g["add_residual"])
+    for D in (64, 128):
+        g = golden_kernels[f"rope_{D}"]
+        cache = L.rope_cache(D, g["max_position"], g["base"])
+        assert torch.equal(cache, g["cos_sin_cache"])
+        assert torch.equal(L.apply_rope(g["positions"], g["q"], cache), g["q_out"])
+        assert torch.equal(L.apply_rope(g["positions"], g["k"], cache), g["k_out"])
+    g = golden_kernels["silu_and_mul"]
+    assert torch.equal(L.silu_and_mul(g["x"]), g["out"])
+
+
+def test_tiny_model_greedy_matches_reference(golden_models):
+    g = golden_models["tiny_qwen3"]
+    cfg = M.ModelCfg()
+    w = M.seeded_weights(cfg, seed=g["seed"], norm_jitter=g["norm_jitter"])
+    tr = M.generate_greedy(w, cfg, g["prompts"], g["max_tokens"], g["block_size"])
+    assert tr.tokens == g["tokens"]
+    assert torch.equal(torch.stack(tr.logits), g["logits"])
+
+
+def test_qwen3_0_6b_config1_matches_reference(golden_models):
+    """BASELINE config 1: full-size random-init Qwen3-0.6B, 1 prompt, block 16, 32 tokens."""
+    g = golden_models["qwen3_0_6b_config1"]
+    cfg = M.ModelCfg.qwen3_0_6b()
+    w = M.seeded_weights(cfg, seed=g["seed"])
+    tr = M.generate_greedy(w, cfg, g["prompts"], g["max_tokens"], g["block_size"])
+    assert tr.tokens == g["tokens"]
+    lg = torch.stack(tr.logits)[:, 0]
+    top = lg.topk(8, dim=-1)
+    assert torch.equal(top.indices, g["top_indices"])
+    assert torch.equal(top.values, g["top_values"])
