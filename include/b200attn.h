@@ -180,12 +180,15 @@ int b200_silu_and_mul(void* out, const void* x, int32_t rows, int32_t inter, int
  * round trip. Replaces layers/sampler.py:9-17 for the greedy parity path (argmax) and
  * for temperature sampling via the Gumbel-max trick with a counter-based RNG.
  * logits: [rows, vocab] in dtype (row stride logits_stride elements);
- * temperatures: [rows] fp32 or NULL (=> argmax). out_tokens: [rows] int64.
+ * temperatures: [rows] fp32 or NULL; a row whose temperature is NULL/<= 0 takes the argmax.
+ * out_tokens: [rows] int64. step_offset: optional DEVICE int64 added to `step` at run time, so
+ * a captured CUDA graph draws fresh randomness on every replay (NULL = none).
  * Gumbel sampling draws the same distribution as softmax+multinomial but not the same
  * random stream as torch.multinomial; only the argmax form is bit-comparable. */
 int b200_sample(int64_t* out_tokens, const void* logits, const float* temperatures,
                 int32_t rows, int32_t vocab, int64_t logits_stride, uint64_t seed,
-                uint64_t step, int32_t dtype, b200_stream_t stream);
+                uint64_t step, const int64_t* step_offset, int32_t dtype,
+                b200_stream_t stream);
 
 #ifdef __cplusplus
 }

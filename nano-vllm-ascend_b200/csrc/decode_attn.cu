@@ -393,39 +393,62 @@ paged_decode_kernel(const __grid_constant__ CUtensorMap tmK,
   }
 }
 
-// Combine kernel: one CTA per (sequence, head group); merges the partial results of items whose
-// tiles were split across CTAs. Items handled by a single CTA were written directly: exit.
+// Combine kernel: one CTA per (item = sequence x head group, output row); merges the partial
+// results of items whose tiles were split across CTAs. Items handled by a single CTA were
+// written directly: exit. Each of the 4 warps folds a strided subset of the partials with
+// coalesced row loads (lane = D/32 consecutive columns), then warp 0 folds the 4 warps.
 template <typename T, int D>
 __global__ void __launch_bounds__(128)
 decode_combine_kernel(const DecodeParams p, int rows /* = HKV_CTA*G */) {
-  const int it = blockIdx.x;
+  constexpr int V = D / 32;  // columns per lane
+  __shared__ float s_acc[4][D];
+  __shared__ float s_ml[4][2];
+  const int it = blockIdx.x, r = blockIdx.y;
   const int items = p.batch * p.hg_count;
   const int t0 = p.header[it], t1 = p.header[it + 1];
   const int per = p.header[items + 1];
   if (t1 == t0) return;
   const int c_first = t0 / per, c_last = (t1 - 1) / per;
   if (c_first == c_last) return;
-  const int b = it / p.hg_count, hg = it - b * p.hg_count;
-  T* obase = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_stride + (int64_t)hg * rows * D;
-  for (int e = threadIdx.x; e < rows * (D / 2); e += blockDim.x) {
-    const int r = e / (D / 2), d = (e - r * (D / 2)) * 2;
-    float m = -INFINITY;
-    for (int c = c_first; c <= c_last; ++c) {
-      const int slot = 2 * c + ((c * per >= t0) ? 0 : 1);
-      m = fmaxf(m, p.part_ml[((int64_t)slot * rows + r) * 2]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = -INFINITY, l = 0.f, acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  for (int c = c_first + warp; c <= c_last; c += 4) {
+    const int slot = 2 * c + ((c * per >= t0) ? 0 : 1);
+    const float* ml = p.part_ml + ((int64_t)slot * rows + r) * 2;
+    const float* po = p.part_o + ((int64_t)slot * rows + r) * D + lane * V;
+    const float mc = ml[0], lc = ml[1];
+    const float m_new = fmaxf(m, mc);
+    const float a = ex2_approx(m - m_new), b = ex2_approx(mc - m_new);
+    l = l * a + lc * b;
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = acc[i] * a + po[i] * b;
+    m = m_new;
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) s_acc[warp][lane * V + i] = acc[i];
+  if (lane == 0) s_ml[warp][0] = m, s_ml[warp][1] = l;
+  __syncthreads();
+  if (warp == 0) {
+    float M = fmaxf(fmaxf(s_ml[0][0], s_ml[1][0]), fmaxf(s_ml[2][0], s_ml[3][0]));
+    float L = 0.f, o[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float sc = ex2_approx(s_ml[w][0] - M);  // exp2(-inf) == 0 for idle warps
+      L = fmaf(s_ml[w][1], sc, L);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = fmaf(s_acc[w][lane * V + i], sc, o[i]);
     }
-    float l = 0.f, ox = 0.f, oy = 0.f;
-    for (int c = c_first; c <= c_last; ++c) {
-      const int slot = 2 * c + ((c * per >= t0) ? 0 : 1);
-      const float* ml = p.part_ml + ((int64_t)slot * rows + r) * 2;
-      const float w = ex2_approx(ml[0] - m);
-      const float2 o2 = *reinterpret_cast<const float2*>(p.part_o + ((int64_t)slot * rows + r) * D + d);
-      l = fmaf(ml[1], w, l);
-      ox = fmaf(o2.x, w, ox);
-      oy = fmaf(o2.y, w, oy);
-    }
-    const float inv = 1.f / l;
-    *reinterpret_cast<uint32_t*>(obase + r * D + d) = pack2<T>(ox * inv, oy * inv);
+    const float inv = 1.f / L;
+    const int b = it / p.hg_count, hg = it - b * p.hg_count;
+    T* orow = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_stride + ((int64_t)hg * rows + r) * D +
+              lane * V;
+#pragma unroll
+    for (int i = 0; i < V; i += 2)
+      *reinterpret_cast<uint32_t*>(orow + i) = pack2<T>(o[i] * inv, o[i + 1] * inv);
   }
 }
 
@@ -530,7 +553,7 @@ static int decode_launch_t(const CUtensorMap& mk, const CUtensorMap& mv, const D
     attr_set = true;
   }
   kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
-  decode_combine_kernel<T, D><<<items, 128, 0, stream>>>(p, HKV_CTA * p.G);
+  decode_combine_kernel<T, D><<<dim3(items, HKV_CTA * p.G), 128, 0, stream>>>(p, HKV_CTA * p.G);
   return finish_launch(2);
 }
 

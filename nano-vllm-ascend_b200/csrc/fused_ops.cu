@@ -289,13 +289,15 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 sample_kernel(int64_t* __restrict__ out, const T* __restrict__ logits,
               const float* __restrict__ temperatures, int vocab, int64_t stride, uint64_t seed,
-              uint64_t step) {
+              uint64_t step, const int64_t* __restrict__ step_offset) {
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   const int row = blockIdx.x;
   const T* lrow = logits + (int64_t)row * stride;
-  const bool greedy = temperatures == nullptr;
-  const float inv_t = greedy ? 1.f : 1.f / temperatures[row];
+  const float temp = temperatures == nullptr ? 0.f : temperatures[row];
+  const bool greedy = !(temp > 0.f);   // no temperatures, or a non-positive one => argmax
+  const float inv_t = greedy ? 1.f : 1.f / temp;
+  if (step_offset != nullptr) step += (uint64_t)*step_offset;
   const uint64_t key = splitmix64(seed ^ splitmix64(step * 0x100000001B3ull + row));
   float best = -INFINITY;
   int best_i = 0x7fffffff;
@@ -376,7 +378,7 @@ extern "C" int b200_qknorm_rope_cache(void* qkv, const int64_t* positions,
                                       int32_t max_position, int32_t num_blocks,
                                       int32_t block_size, int32_t dtype, b200_stream_t stream) {
   B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
-  B200_RETURN_IF(num_tokens < 0 || num_heads <= 0 || num_kv_heads <= 0 || max_position <= 0,
+  B200_RETURN_IF(num_tokens < 0 || num_heads <= 0 || num_kv_heads < 0 || max_position <= 0,
                  B200_ERR_BAD_SHAPE);
   B200_RETURN_IF(head_dim != 64 && head_dim != 128, B200_ERR_UNSUPPORTED);
   if (num_tokens == 0) return B200_OK;
@@ -403,16 +405,18 @@ extern "C" int b200_qknorm_rope_cache(void* qkv, const int64_t* positions,
 
 extern "C" int b200_sample(int64_t* out_tokens, const void* logits, const float* temperatures,
                            int32_t rows, int32_t vocab, int64_t logits_stride, uint64_t seed,
-                           uint64_t step, int32_t dtype, b200_stream_t stream) {
+                           uint64_t step, const int64_t* step_offset, int32_t dtype,
+                           b200_stream_t stream) {
   B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
   B200_RETURN_IF(rows < 0 || vocab <= 0 || logits_stride < vocab, B200_ERR_BAD_SHAPE);
   if (rows == 0) return B200_OK;
   B200_RETURN_IF(!out_tokens || !logits, B200_ERR_NULL_POINTER);
   if (dtype == B200_DTYPE_BF16)
     sample_kernel<__nv_bfloat16><<<rows, 1024, 0, (cudaStream_t)stream>>>(
-        out_tokens, (const __nv_bfloat16*)logits, temperatures, vocab, logits_stride, seed, step);
+        out_tokens, (const __nv_bfloat16*)logits, temperatures, vocab, logits_stride, seed, step,
+        step_offset);
   else
     sample_kernel<__half><<<rows, 1024, 0, (cudaStream_t)stream>>>(
-        out_tokens, (const __half*)logits, temperatures, vocab, logits_stride, seed, step);
+        out_tokens, (const __half*)logits, temperatures, vocab, logits_stride, seed, step, step_offset);
   return finish_launch();
 }

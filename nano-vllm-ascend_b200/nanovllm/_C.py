@@ -49,7 +49,7 @@ PROTOTYPES = {
                                    c_int32, c_void_p]),
     "b200_silu_and_mul": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b200_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_uint64,
-                              c_uint64, c_int32, c_void_p]),
+                              c_uint64, c_void_p, c_int32, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,101 @@
+"""Engine configuration (reference: config.py:14-60). Field names are kept; ``device`` is
+"cuda", ``hccl_port`` is the TCP rendezvous port of the NCCL process group, ``graph_mode``
+selects eager vs CUDA-graph decode. ``model`` may be a checkpoint directory (HF layout), or
+the name of a built-in architecture preset (random-init weights, for synthetic benchmarks
+where no checkpoint can be downloaded)."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from enum import Enum
+
+
+class GraphMode(Enum):
+    EAGER = "eager"
+    CUDA_GRAPH = "cuda-graph"
+    # accepted aliases of the reference's Ascend modes: both mean "replay a captured step"
+    MAX_AUTOTUNE = "max-autotune"
+    REDUCE_OVERHEAD = "reduce-overhead"
+
+
+def preset_hf_config(name: str):
+    """Architecture presets built offline from the public model cards."""
+    from transformers import LlamaConfig, Qwen3Config
+    key = name.lower().rstrip("/").split("/")[-1]
+    if key == "qwen3-0.6b":
+        c = Qwen3Config(vocab_size=151936, hidden_size=1024, num_hidden_layers=28,
+                        num_attention_heads=16, num_key_value_heads=8, head_dim=128,
+                        intermediate_size=3072, rms_norm_eps=1e-6, max_position_embeddings=40960,
+                        tie_word_embeddings=True, attention_bias=False, rope_theta=1000000.0)
+    elif key == "qwen3-32b":
+        c = Qwen3Config(vocab_size=151936, hidden_size=5120, num_hidden_layers=64,
+                        num_attention_heads=64, num_key_value_heads=8, head_dim=128,
+                        intermediate_size=25600, rms_norm_eps=1e-6, max_position_embeddings=40960,
+                        tie_word_embeddings=False, attention_bias=False, rope_theta=1000000.0)
+    elif key == "llama-3.2-1b":
+        c = LlamaConfig(vocab_size=128256, hidden_size=2048, num_hidden_layers=16,
+                        num_attention_heads=32, num_key_value_heads=8, head_dim=64,
+                        intermediate_size=8192, rms_norm_eps=1e-5, max_position_embeddings=131072,
+                        tie_word_embeddings=True, rope_theta=500000.0)
+    elif key == "tiny-qwen3":
+        c = Qwen3Config(vocab_size=512, hidden_size=128, num_hidden_layers=2,
+                        num_attention_heads=4, num_key_value_heads=2, head_dim=64,
+                        intermediate_size=256, rms_norm_eps=1e-6, max_position_embeddings=512,
+                        tie_word_embeddings=True, attention_bias=False, rope_theta=1000000.0)
+    else:
+        return None
+    c.architectures = ["LlamaForCausalLM" if "llama" in key else "Qwen3ForCausalLM"]
+    c.dtype = "bfloat16"
+    c.eos_token_id = -1 if key == "tiny-qwen3" else c.eos_token_id
+    return c
+
+
+@dataclass
+class Config:
+    model: str
+    max_num_batched_tokens: int = 16384
+    max_num_seqs: int = 256
+    max_model_len: int = 4096
+    gpu_memory_utilization: float = 0.7
+    tensor_parallel_size: int = 1
+    enforce_eager: bool = False
+    hf_config: object | None = None
+    eos: int = -1
+    kvcache_block_size: int = 256
+    num_kvcache_blocks: int = -1
+    use_graph_cache: bool = False
+    hccl_port: int = 28000
+    graph_mode: str = GraphMode.CUDA_GRAPH.value
+    is_multimodal: bool = False
+    trust_remote_code: bool = False
+    # additions (all optional; defaults keep the reference behaviour)
+    seed: int = 0                      # random-init / sampler seed
+    norm_jitter: float = 0.0           # random-init only
+    load_weights: bool | None = None   # None: load iff *.safetensors exist under `model`
+    distributed_launch: str = "spawn"  # "spawn": reference style (rank 0 spawns workers);
+                                       # "env": every rank is already running (torchrun/SPMD)
+    prefix_hit_prefill: bool = False   # feed only uncached prompt tokens (attention_ori semantics)
+    device = "cuda"
+
+    def __post_init__(self):
+        assert self.kvcache_block_size % 16 == 0
+        assert 1 <= self.tensor_parallel_size <= 8
+        if self.hf_config is None:
+            if os.path.isdir(self.model):
+                from transformers import AutoConfig
+                self.hf_config = AutoConfig.from_pretrained(self.model,
+                                                            trust_remote_code=self.trust_remote_code)
+            else:
+                self.hf_config = preset_hf_config(self.model)
+                assert self.hf_config is not None, (
+                    f"{self.model!r} is neither a checkpoint directory nor a known preset")
+        text_config = getattr(self.hf_config, "text_config", self.hf_config)
+        max_pos = getattr(text_config, "max_position_embeddings", None)
+        if max_pos is not None:
+            self.max_model_len = min(self.max_model_len, max_pos)
+        eos = getattr(text_config, "eos_token_id", None)
+        if isinstance(eos, (list, tuple)):
+            eos = eos[0] if eos else None
+        if eos is not None:
+            self.eos = eos
+        assert self.max_num_batched_tokens >= self.max_model_len

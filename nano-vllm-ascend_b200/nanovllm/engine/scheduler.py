@@ -1,0 +1,88 @@
+"""Prefill-first continuous batching with preemption (reference: engine/scheduler.py)."""
+from __future__ import annotations
+
+from collections import deque
+
+from ..config import Config
+from .block_manager import BlockManager
+from .sequence import FinishReason, Sequence, SequenceStatus
+
+
+class Scheduler:
+
+    def __init__(self, config: Config):
+        self.max_num_seqs = config.max_num_seqs
+        self.max_num_batched_tokens = config.max_num_batched_tokens
+        self.max_model_len = config.max_model_len
+        self.eos = config.eos
+        # the last physical block is the dummy slot padded graph rows write to
+        # (reference scheduler.py:26-30, model_runner.py:310)
+        self.block_manager = BlockManager(config.num_kvcache_blocks - 1, config.kvcache_block_size)
+        self.waiting: deque[Sequence] = deque()
+        self.running: deque[Sequence] = deque()
+
+    def is_finished(self) -> bool:
+        return not self.waiting and not self.running
+
+    def add(self, seq: Sequence) -> None:
+        self.waiting.append(seq)
+
+    def schedule(self) -> tuple[list[Sequence], bool]:
+        batch: list[Sequence] = []
+        tokens = 0
+        # 1) admit waiting prompts while the token budget and free blocks allow
+        while self.waiting and len(batch) < self.max_num_seqs:
+            seq = self.waiting[0]
+            if tokens + len(seq) > self.max_num_batched_tokens or not self.block_manager.can_allocate(seq):
+                break
+            self.waiting.popleft()
+            self.block_manager.allocate(seq)
+            seq.status = SequenceStatus.RUNNING
+            self.running.append(seq)
+            batch.append(seq)
+            tokens += len(seq) - seq.num_cached_tokens
+        if batch:
+            return batch, True
+        # 2) one decode step for as many running sequences as fit; evict from the back on OOM
+        while self.running and len(batch) < self.max_num_seqs:
+            seq = self.running.popleft()
+            while not self.block_manager.can_append(seq):
+                if self.running:
+                    self.preempt(self.running.pop())
+                else:
+                    self.preempt(seq)
+                    seq = None
+                    break
+            if seq is not None:
+                self.block_manager.may_append(seq)
+                batch.append(seq)
+        if batch:
+            self.running.extendleft(reversed(batch))
+        return batch, False
+
+    def preempt(self, seq: Sequence) -> None:
+        seq.status = SequenceStatus.WAITING
+        seq.finish_reason = FinishReason.PREEMPTED
+        self.block_manager.deallocate(seq)
+        self.waiting.appendleft(seq)
+
+    def abort_seq_group(self, request_id: str) -> None:
+        for queue in (self.waiting, self.running):
+            for seq in [s for s in queue if s.request_id == request_id]:
+                queue.remove(seq)
+                self.free_seq(seq, FinishReason.ABORTED)
+
+    def free_seq(self, seq: Sequence, reason: FinishReason) -> None:
+        seq.status = SequenceStatus.FINISHED
+        seq.finish_reason = reason
+        self.block_manager.deallocate(seq)
+
+    def postprocess(self, seqs: list[Sequence], token_ids: list[int]) -> None:
+        for seq, token_id in zip(seqs, token_ids):
+            seq.append_token(token_id)
+            hit_eos = not seq.ignore_eos and token_id == self.eos
+            out_of_room = (seq.num_completion_tokens == seq.max_tokens or
+                           len(seq) == self.max_model_len)
+            if hit_eos or out_of_room:
+                self.free_seq(seq, FinishReason.EOS if hit_eos else FinishReason.LENGTH)
+                self.running.remove(seq)

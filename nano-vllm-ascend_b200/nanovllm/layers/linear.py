@@ -1,0 +1,123 @@
+"""Tensor-parallel linear layers (reference: layers/linear.py).
+
+Same constructors and ``weight_loader(param, tensor[, shard_id])`` signatures. GEMMs stay on
+cuBLAS (``F.linear``). The one collective of a decoder layer is the SUM all-reduce
+of the row-parallel output: NCCL over NVLink/NVSwitch through ``torch.distributed``, issued on
+the current stream so it is captured into the decode CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+
+def tp_rank_size() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def divide(a: int, b: int) -> int:
+    if a % b:
+        raise ValueError(f"{a} is not divisible by the tensor-parallel size {b}")
+    return a // b
+
+
+class LinearBase(nn.Module):
+
+    def __init__(self, input_size, output_size, bias=False, tp_dim=None):
+        super().__init__()
+        self.tp_dim = tp_dim
+        self.tp_rank, self.tp_size = tp_rank_size()
+        self.weight = nn.Parameter(torch.empty(output_size, input_size))
+        self.weight.weight_loader = self.weight_loader
+        if bias:
+            self.bias = nn.Parameter(torch.empty(output_size))
+            self.bias.weight_loader = self.weight_loader
+        else:
+            self.register_parameter("bias", None)
+
+
+class ReplicatedLinear(LinearBase):
+
+    def __init__(self, input_size, output_size, bias=False):
+        super().__init__(input_size, output_size, bias)
+
+    def weight_loader(self, param, loaded_weight):
+        param.data.copy_(loaded_weight)
+
+    def forward(self, x):
+        return F.linear(x, self.weight, self.bias)
+
+
+class ColumnParallelLinear(LinearBase):
+    """Output features sharded across ranks."""
+
+    def __init__(self, input_size, output_size, bias=False):
+        _, tp = tp_rank_size()
+        super().__init__(input_size, divide(output_size, tp), bias, 0)
+
+    def weight_loader(self, param, loaded_weight):
+        n = param.data.size(self.tp_dim)
+        param.data.copy_(loaded_weight.narrow(self.tp_dim, self.tp_rank * n, n))
+
+    def forward(self, x):
+        return F.linear(x, self.weight, self.bias)
+
+
+class MergedColumnParallelLinear(ColumnParallelLinear):
+    """Several column-parallel matrices stacked (gate|up); each is sharded on its own."""
+
+    def __init__(self, input_size, output_sizes, bias=False):
+        self.output_sizes = list(output_sizes)
+        super().__init__(input_size, sum(output_sizes), bias)
+
+    def weight_loader(self, param, loaded_weight, loaded_shard_id: int):
+        start = sum(self.output_sizes[:loaded_shard_id]) // self.tp_size
+        size = self.output_sizes[loaded_shard_id] // self.tp_size
+        piece = loaded_weight.chunk(self.tp_size, self.tp_dim)[self.tp_rank]
+        param.data.narrow(self.tp_dim, start, size).copy_(piece)
+
+
+class QKVParallelLinear(ColumnParallelLinear):
+    """Fused q|k|v projection; each rank holds H/tp query heads and Hkv/tp kv heads."""
+
+    def __init__(self, hidden_size, head_size, total_num_heads, total_num_kv_heads=None, bias=False):
+        _, tp = tp_rank_size()
+        total_num_kv_heads = total_num_kv_heads or total_num_heads
+        self.head_size = head_size
+        self.num_heads = divide(total_num_heads, tp)
+        self.num_kv_heads = divide(total_num_kv_heads, tp)
+        super().__init__(hidden_size, (total_num_heads + 2 * total_num_kv_heads) * head_size, bias)
+
+    def weight_loader(self, param, loaded_weight, loaded_shard_id: str):
+        q_rows = self.num_heads * self.head_size
+        kv_rows = self.num_kv_heads * self.head_size
+        start, size = {"q": (0, q_rows), "k": (q_rows, kv_rows), "v": (q_rows + kv_rows, kv_rows)}[
+            loaded_shard_id]
+        piece = loaded_weight.chunk(self.tp_size, self.tp_dim)[self.tp_rank]
+        param.data.narrow(self.tp_dim, start, size).copy_(piece)
+
+
+class RowParallelLinear(LinearBase):
+    """Input features sharded; partial products are summed across ranks (the layer's only
+    collective, reference linear.py:149-153). Bias is added on rank 0 only, before the sum."""
+
+    def __init__(self, input_size, output_size, bias=False):
+        _, tp = tp_rank_size()
+        super().__init__(divide(input_size, tp), output_size, bias, 1)
+
+    def weight_loader(self, param, loaded_weight):
+        if param.dim() <= self.tp_dim:          # bias: replicated, applied on rank 0 only
+            param.data.copy_(loaded_weight)
+            return
+        n = param.data.size(self.tp_dim)
+        param.data.copy_(loaded_weight.narrow(self.tp_dim, self.tp_rank * n, n))
+
+    def forward(self, x):
+        y = F.linear(x, self.weight, self.bias if self.tp_rank == 0 else None)
+        if self.tp_size > 1:
+            dist.all_reduce(y)
+        return y

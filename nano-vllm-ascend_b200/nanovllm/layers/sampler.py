@@ -1,0 +1,33 @@
+"""Sampling tail (reference: layers/sampler.py:9-17).
+
+Reference semantics: trim padded graph rows, divide by temperature, softmax, multinomial.
+Here the whole tail is one kernel over the bf16 logits: Gumbel-max sampling
+draws from exactly softmax(logits / T) without materialising fp32 logits or probabilities;
+``greedy=True`` (temperature <= 0 is still rejected by SamplingParams, as in the reference)
+gives the argmax used by the parity tests.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class Sampler(nn.Module):
+
+    def __init__(self, seed: int = 0):
+        super().__init__()
+        self.seed = seed
+        self.step = 0
+
+    def forward(self, logits: torch.Tensor, temperatures: torch.Tensor | None, greedy: bool = False,
+                out: torch.Tensor | None = None, step_offset: torch.Tensor | None = None):
+        """temperatures: [real_bs] fp32; rows with temperature <= 0 (or greedy=True) take the
+        argmax. step_offset: device int64 counter (CUDA-graph replays advance it)."""
+        real_bs = logits.shape[0] if temperatures is None else temperatures.shape[0]
+        if logits.shape[0] != real_bs:
+            logits = logits[:real_bs]
+        self.step += 1
+        return ops.sample(logits, None if greedy else temperatures, seed=self.seed, step=self.step,
+                          out=out, step_offset=step_offset)

@@ -219,9 +219,10 @@ def silu_and_mul(x, out=None):
     return out
 
 
-def sample(logits, temperatures=None, seed=0, step=0, out=None):
-    """argmax (temperatures=None) or Gumbel-max sampling over [rows, vocab] bf16/fp16 logits."""
-    _need_cuda(logits, temperatures)
+def sample(logits, temperatures=None, seed=0, step=0, out=None, step_offset=None):
+    """argmax (temperatures=None or <= 0) or Gumbel-max sampling over [rows, vocab] bf16/fp16
+    logits. step_offset: optional device int64 scalar added to `step` when the kernel runs."""
+    _need_cuda(logits, temperatures, step_offset)
     rows, vocab = logits.shape
     if logits.stride(1) != 1:
         raise ValueError("logits must have unit inner stride")
@@ -232,5 +233,6 @@ def sample(logits, temperatures=None, seed=0, step=0, out=None):
         out = torch.empty(rows, dtype=torch.int64, device=logits.device)
     _C.check(_C.load().b200_sample(out.data_ptr(), logits.data_ptr(), _ptr(temperatures), rows,
                                    vocab, logits.stride(0) if rows > 1 else vocab, int(seed),
-                                   int(step), _dt(logits), _stream()), "b200_sample")
+                                   int(step), _ptr(step_offset), _dt(logits), _stream()),
+             "b200_sample")
     return out

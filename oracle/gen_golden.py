@@ -227,6 +227,49 @@ def gen_models():
     return out
 
 
+def gen_scheduler_trace():
+    """Drive the reference's own Scheduler + BlockManager (engine/scheduler.py,
+    engine/block_manager.py, imported unmodified) through a seeded workload that exercises
+    prefix sharing, block growth, finishing and preemption; record every step's decision."""
+    from types import SimpleNamespace
+    from nanovllm.engine.scheduler import Scheduler
+    from nanovllm.engine.sequence import Sequence
+    from nanovllm.sampling_params import SamplingParams
+    traces = {}
+    for name, nb, bs, max_seqs, budget in (("roomy", 64, 16, 8, 256), ("tight", 14, 16, 6, 128)):
+        cfg = SimpleNamespace(max_num_seqs=max_seqs, max_num_batched_tokens=budget, eos=7,
+                              num_kvcache_blocks=nb, kvcache_block_size=bs, is_multimodal=False,
+                              hf_config=None, max_model_len=200)
+        sched = Scheduler(cfg)
+        rnd = random.Random(42)
+        shared = [rnd.randint(10, 99) for _ in range(40)]
+        reqs, seqs = [], []
+        for i in range(12):
+            prompt = (shared[:rnd.choice([16, 32, 40])] if i % 3 == 0 else []) + \
+                [rnd.randint(10, 99) for _ in range(rnd.randint(1, 30))]
+            sp = dict(temperature=0.6, max_tokens=rnd.randint(1, 40), ignore_eos=(i % 4 != 0))
+            reqs.append(dict(prompt=prompt, **sp))
+            s = Sequence(prompt, SamplingParams(**sp), block_size=bs)
+            seqs.append(s)
+            sched.add(s)
+        index = {s.seq_id: i for i, s in enumerate(seqs)}
+        steps = []
+        tok_rnd = random.Random(1)
+        while not sched.is_finished() and len(steps) < 2000:
+            batch, is_prefill = sched.schedule()
+            rec = dict(is_prefill=is_prefill,
+                       seqs=[(index[s.seq_id], list(s.block_table), s.num_cached_tokens, len(s)) for s in batch])
+            toks = [tok_rnd.randint(5, 12) for _ in batch]     # 7 == eos shows up now and then
+            rec["tokens"] = toks
+            sched.postprocess(batch, toks)
+            rec["finished"] = [index[s.seq_id] for s in batch if s.is_finished]
+            steps.append(rec)
+        traces[name] = dict(num_blocks=nb, block_size=bs, max_num_seqs=max_seqs,
+                            max_num_batched_tokens=budget, eos=7, max_model_len=200,
+                            requests=reqs, steps=steps)
+    return traces
+
+
 def main():
     torch.manual_seed(0)
     native, _ = import_reference()
@@ -235,7 +278,10 @@ def main():
     torch.save(k, os.path.join(OUT, "kernels.pt"))
     m = gen_models()
     torch.save(m, os.path.join(OUT, "models.pt"))
-    for name in ("kernels.pt", "models.pt"):
+    tr = gen_scheduler_trace()
+    torch.save(tr, os.path.join(OUT, "scheduler.pt"))
+    print({k: len(v["steps"]) for k, v in tr.items()})
+    for name in ("kernels.pt", "models.pt", "scheduler.pt"):
         print(name, os.path.getsize(os.path.join(OUT, name)), "bytes")
     print("tiny tokens", m["tiny_qwen3"]["tokens"])
     print("0.6B tokens", m["qwen3_0_6b_config1"]["tokens"])

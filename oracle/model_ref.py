@@ -42,11 +42,12 @@ class ModelCfg:
 
     @staticmethod
     def llama_3_2_1b():
-        # models/llama.py reads rope_theta with a 10000 fallback (llama.py:133) which is what
-        # transformers>=5 configs trigger (SURVEY.md 8c "oracle quirks").
+        # rope_theta: the model card's 500000. (Under transformers>=5 the reference's
+        # getattr(config, "rope_theta", 10000) at llama.py:133 falls back to 10000; the base is
+        # an input of this oracle, parity tests pass the same value to both sides.)
         return ModelCfg(vocab_size=128256, hidden_size=2048, num_layers=16, num_heads=32,
                         num_kv_heads=8, head_dim=64, intermediate_size=8192, rms_eps=1e-5,
-                        rope_theta=10000.0, max_position=131072, qk_norm=False)
+                        rope_theta=500000.0, max_position=131072, qk_norm=False)
 
 
 def param_shapes(cfg: ModelCfg) -> dict[str, tuple[int, ...]]:
@@ -97,7 +98,7 @@ class StepMeta:
 
 
 def forward(w, cfg: ModelCfg, input_ids, positions, meta: StepMeta, kv_cache, block_size,
-            attn_mode="reference", return_hidden=False):
+            attn_mode="reference", return_hidden=False, trace: dict | None = None):
     """One model step. kv_cache: [2, L, nb, bs, Hkv, D] (written in place).
     Mirrors Qwen3Model.forward (qwen3.py:175-185) / Qwen3DecoderLayer.forward (:148-161) /
     Qwen3Attention.forward (:74-90) / Qwen3MLP.forward (:115-119) / compute_logits (:216-218)."""
@@ -111,7 +112,11 @@ def forward(w, cfg: ModelCfg, input_ids, positions, meta: StepMeta, kv_cache, bl
             residual, x = x, L.rmsnorm(x, w[p + "input_layernorm.weight"], cfg.rms_eps)
         else:
             x, residual = L.add_rmsnorm(x, residual, w[p + "input_layernorm.weight"], cfg.rms_eps)
+        if trace is not None:
+            trace[p + "attn_in"] = x
         qkv = F.linear(x, w[p + "self_attn.qkv_proj.weight"])
+        if trace is not None:
+            trace[p + "qkv"] = qkv
         q, k, v = L.qkv_epilogue(qkv, positions, cos_sin,
                                  w.get(p + "self_attn.q_norm.weight"),
                                  w.get(p + "self_attn.k_norm.weight"), cfg.rms_eps, H, G, D)
@@ -124,11 +129,19 @@ def forward(w, cfg: ModelCfg, input_ids, positions, meta: StepMeta, kv_cache, bl
             o = A.decode_attention(q, kc, vc, meta.context_lens, meta.block_tables, G, D,
                                    mode=attn_mode)
         o = o.to(cfg.dtype)
+        if trace is not None:
+            trace[p + "q"], trace[p + "k"], trace[p + "attn_out"] = q, k, o
         x = F.linear(o, w[p + "self_attn.o_proj.weight"])
+        if trace is not None:
+            trace[p + "o_proj"] = x
         x, residual = L.add_rmsnorm(x, residual, w[p + "post_attention_layernorm.weight"],
                                     cfg.rms_eps)
+        if trace is not None:
+            trace[p + "mlp_in"] = x
         x = F.linear(x, w[p + "mlp.gate_up_proj.weight"])
         x = F.linear(L.silu_and_mul(x), w[p + "mlp.down_proj.weight"])
+        if trace is not None:
+            trace[p + "mlp_out"] = x
     x, _ = L.add_rmsnorm(x, residual, w["model.norm.weight"], cfg.rms_eps)
     if return_hidden:
         return x

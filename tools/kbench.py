@@ -1,0 +1,81 @@
+"""Developer micro-benchmark of single kernels (not the contract bench; see bench.py).
+usage: python tools/kbench.py [decode|prefill|all] [--bs 16]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "nano-vllm-ascend_b200"))
+from nanovllm import ops  # noqa: E402
+
+
+def timeit(fn, iters=20, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_decode(B, H, G, D, bs, ctx, ctas=0):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nblk = B * ((ctx + bs - 1) // bs)
+    kc = torch.randn(nblk + 1, bs, G * D, device="cuda", generator=g).to(torch.bfloat16)
+    vc = torch.randn(nblk + 1, bs, G * D, device="cuda", generator=g).to(torch.bfloat16)
+    q = torch.randn(B, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    bt = torch.randperm(nblk, device="cuda", generator=g).to(torch.int32).view(B, -1).contiguous()
+    cl = torch.full((B,), ctx, dtype=torch.int32, device="cuda")
+    out = torch.empty(B, H * D, dtype=torch.bfloat16, device="cuda")
+    ws = ops.decode_workspace(B, H, G, D, q.device)
+    fn = lambda: ops.paged_decode_attn(q, kc, vc, bt, cl, D ** -0.5, G, out=out, workspace=ws,
+                                       num_ctas=ctas)
+    med, best = timeit(fn)
+    byts = B * ctx * 2 * G * D * 2
+    return dict(kernel="paged_decode", B=B, H=H, G=G, D=D, bs=bs, ctx=ctx, ctas=ctas,
+                ms_med=round(med, 4), ms_best=round(best, 4), GBps_med=round(byts / med / 1e6, 1),
+                GBps_best=round(byts / best / 1e6, 1))
+
+
+def bench_prefill(nseq, L, H, G, D):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    T = nseq * L
+    qkv = torch.randn(T, (H + 2 * G) * D, device="cuda", generator=g).to(torch.bfloat16)
+    q = qkv[:, :H * D].unflatten(1, (H, D))
+    k = qkv[:, H * D:(H + G) * D].unflatten(1, (G, D))
+    v = qkv[:, (H + G) * D:].unflatten(1, (G, D))
+    cu = torch.arange(0, T + 1, L, dtype=torch.int32, device="cuda")
+    out = torch.empty(T, H * D, dtype=torch.bfloat16, device="cuda")
+    fn = lambda: ops.prefill_varlen_attn(q, k, v, cu, cu, L, L, D ** -0.5, G, out=out)
+    med, best = timeit(fn, iters=10, warmup=3)
+    flops = 2 * L * L * H * D * nseq  # causal: 4*L*L*H*D/2
+    return dict(kernel="prefill", nseq=nseq, L=L, H=H, G=G, D=D, ms_med=round(med, 4),
+                TFLOPs_med=round(flops / med / 1e9, 1), TFLOPs_best=round(flops / best / 1e9, 1))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    args = ap.parse_args()
+    res = []
+    if args.what in ("decode", "all"):
+        for bs in (16, 256):
+            res.append(bench_decode(256, 16, 8, 128, bs, 1024))
+        res.append(bench_decode(256, 16, 8, 128, 16, 1024, ctas=296))
+        res.append(bench_decode(256, 8, 1, 128, 16, 1024))      # 32B TP=8 per-rank shape
+        res.append(bench_decode(256, 32, 8, 64, 16, 1024))      # Llama-1B
+        res.append(bench_decode(1, 16, 8, 128, 16, 8192))
+        res.append(bench_decode(16, 16, 8, 128, 16, 1024))
+    if args.what in ("prefill", "all"):
+        res.append(bench_prefill(16, 1024, 16, 8, 128))
+        res.append(bench_prefill(1, 8192, 32, 8, 64))
+    for r in res:
+        print(json.dumps(r))
