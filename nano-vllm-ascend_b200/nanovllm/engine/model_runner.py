@@ -64,6 +64,8 @@ class ModelRunner:
             else:
                 dist.init_process_group("nccl", f"tcp://127.0.0.1:{config.hccl_port}",
                                         world_size=self.world_size, rank=rank)
+        from ..layers.linear import set_tp_world
+        set_tp_world(0, 1) if self.world_size == 1 else set_tp_world(None)
         local = int(os.environ.get("LOCAL_RANK", rank)) if self.spmd else rank
         self.device = torch.device("cuda", local if self.world_size > 1 or self.spmd else
                                    torch.cuda.current_device())
@@ -248,7 +250,8 @@ class ModelRunner:
         self.d_out = torch.zeros(B, dtype=torch.int64, device=self.device)
         self.h_out = torch.zeros(B, dtype=torch.int64, pin_memory=True)
         self.d_rng = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self._tables_dirty_rows = 0
+        self.h2d_bytes = self.d2h_bytes = 0        # decode-step traffic counters (bench.py e2e)
+        self.launches_per_graph: dict[int, int] = {}
 
     def _stage_decode(self, seqs: list[Sequence], padded: int):
         """Fill the pinned staging buffer for a decode step and upload it with one copy
@@ -293,6 +296,7 @@ class ModelRunner:
                 dirty_hi = i + 1
         nbytes = self._head_bytes + dirty_hi * self.max_blocks * 4
         self._stage_dev[:nbytes].copy_(self._stage_host[:nbytes], non_blocking=True)
+        self.h2d_bytes += nbytes
 
     def _set_decode_context(self, bs: int, real_bs: int):
         set_context(False, slot_mapping=self.d_slots[:bs], context_lens=self.d_ctx[:bs],
@@ -324,8 +328,11 @@ class ModelRunner:
             self._decode_step(bs)                      # warm-up (allocator, cuBLAS heuristics)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            from .. import ops
+            before = ops.launch_count()
             with torch.cuda.graph(graph, pool=pool):
                 self._decode_step(bs)
+            self.launches_per_graph[bs] = ops.launch_count() - before
             pool = pool or graph.pool()
             self.graphs[bs] = graph
         reset_context()
@@ -360,5 +367,6 @@ class ModelRunner:
             self._decode_step(bs)
             reset_context()
         self.h_out[:n].copy_(self.d_out[:n], non_blocking=True)
+        self.d2h_bytes += n * 8
         torch.cuda.current_stream().synchronize()
         return self.h_out[:n].tolist()

@@ -13,7 +13,20 @@ import torch.nn.functional as F
 from torch import nn
 
 
+_TP_OVERRIDE: tuple[int, int] | None = None
+
+
+def set_tp_world(rank: int | None, size: int | None = None) -> None:
+    """Pin the tensor-parallel (rank, size) the layers shard by. ``None`` restores the
+    reference behaviour (the default process group's rank/size, linear.py:23-24). The runner
+    pins (0, 1) for data-parallel replicas that share a process group only for timing."""
+    global _TP_OVERRIDE
+    _TP_OVERRIDE = None if rank is None else (int(rank), int(size))
+
+
 def tp_rank_size() -> tuple[int, int]:
+    if _TP_OVERRIDE is not None:
+        return _TP_OVERRIDE
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
