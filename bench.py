@@ -175,8 +175,16 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------ the GPU arm
+def dbg(rank, *a):
+    if os.environ.get("B200_BENCH_DEBUG"):
+        print(f"[bench rank{rank} {time.strftime('%X')}]", *a, file=sys.stderr, flush=True)
+
+
 def main():
     args = parse_args()
+    if os.environ.get("B200_BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["B200_BENCH_DEBUG"]), exit=True)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -217,6 +225,7 @@ def main():
         return float(t.item())
 
     clocks = ClockSampler(local)
+    dbg(rank, 'engine built')
     # ---- phase 1: submit everything at t=0, prefill (TTFT)
     barrier()
     clocks.start()
@@ -230,6 +239,7 @@ def main():
     ttft_p50 = ttfts[len(ttfts) // 2]
     prefill_s = ttfts[-1] / 1e3
 
+    dbg(rank, 'prefill done')
     # ---- phase 2: e2e decode through the public API (host buffers, H2D + D2H inside)
     for _ in range(W):
         llm.step()
@@ -250,6 +260,7 @@ def main():
     d2h_per = (runner.d2h_bytes - d2h0) / K
     ctx_now = ctx + W + K            # context length the resident buffers now describe
 
+    dbg(rank, 'e2e done')
     # ---- phase 3: device-only: replay the captured step with its inputs resident in HBM
     graph = runner.graphs[B]
     for _ in range(W):
@@ -263,6 +274,7 @@ def main():
     dev_s = max_over_ranks(e0.elapsed_time(e1) / 1e3)
     launches = runner.launches_per_graph.get(B, 0) * K
 
+    dbg(rank, 'replay done')
     # ---- phase 4: the dominant kernel alone, all layers' caches (cold in L2), CUDA events
     Hq, Hkv, D = spec.num_heads // (world if args.tp else 1), spec.num_kv_heads // (world if args.tp else 1), spec.head_dim
     q = torch.randn(B, Hq, D, device="cuda", dtype=runner.dtype)
@@ -284,6 +296,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     attn_launch_s = e0.elapsed_time(e1) / 1e3 / (reps * L)
+    dbg(rank, 'attn loop done')
     clk = clocks.stop()
     ctx_sum = int(runner.d_ctx[:B].sum().item())
     attn_bytes = ctx_sum * 2 * Hkv * D * runner.dtype.itemsize          # algorithmic bytes / launch
@@ -322,12 +335,18 @@ def main():
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{args.cpu_sample_seqs} of {B} sequences, one full 28-layer decode "
                                           f"step at ctx={ctx}, 3 timed steps of {sec:.1f} s each"}
+    dbg(rank, 'before exit')
     llm.exit()
+    dbg(rank, 'after exit')
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        # destroy_process_group() can block for minutes once CUDA graphs that embedded NCCL kernels
+        # have been replayed; everything is measured and printed, so leave without the teardown
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

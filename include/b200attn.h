@@ -124,6 +124,8 @@ int b200_paged_decode_attn(void* out, const void* q, const void* k_cache, const 
  * Paged K/V mode (block_tables != NULL, the prefix-cache-hit form of attention_ori.py:65-66):
  *   k/v are the paged caches [num_blocks, block_size, num_kv_heads*head_dim]; sequence i's
  *   keys are its first (cu_seqlens_k[i+1]-cu_seqlens_k[i]) cached tokens via block_tables[i].
+ * total_q / total_k: number of packed rows in q / in k,v (= cu_seqlens[num_seqs]; bounds of the
+ * TMA tensor maps; total_k is ignored in paged mode).
  * Causal mask is bottom-right aligned (query row r of a sequence with Lq queries and Lk keys
  * sees keys 0 .. r + Lk - Lq), == NPU sparse_mode=3 and flash-attn causal; identical to the
  * oracle's top-left mask whenever Lq == Lk, which is the only case the reference runner
@@ -131,7 +133,8 @@ int b200_paged_decode_attn(void* out, const void* q, const void* k_cache, const 
  * ------------------------------------------------------------------------------- */
 int b200_prefill_varlen_attn(void* out, const void* q, const void* k, const void* v,
                              const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
-                             int32_t num_seqs, int32_t max_seqlen_q, int32_t max_seqlen_k,
+                             int32_t num_seqs, int32_t total_q, int32_t total_k,
+                             int32_t max_seqlen_q, int32_t max_seqlen_k,
                              int32_t num_heads, int32_t num_kv_heads, int32_t head_dim,
                              int64_t q_stride, int64_t k_stride, int64_t v_stride,
                              int64_t out_stride, const int32_t* block_tables,

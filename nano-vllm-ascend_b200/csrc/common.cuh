@@ -25,6 +25,10 @@ inline int finish_launch(int kernels = 1) {
   return B200_OK;
 }
 
+// TMA tensor map (cached by key) over a row-major 16-bit matrix; see decode_attn.cu
+int get_panel_map(const void* base, int64_t rows, int64_t row_bytes, int chunks, int rows_box,
+                  int chunks_box, int dtype, CUtensorMap* out);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------- dtype traits

@@ -473,29 +473,30 @@ static EncodeTiledFn get_encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  int64_t rows;
+  int64_t rows, row_bytes;
   int chunks, rows_box, chunks_box, dtype;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && chunks == o.chunks && rows_box == o.rows_box &&
-           chunks_box == o.chunks_box && dtype == o.dtype;
+    return ptr == o.ptr && rows == o.rows && row_bytes == o.row_bytes && chunks == o.chunks &&
+           rows_box == o.rows_box && chunks_box == o.chunks_box && dtype == o.dtype;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
-    h ^= std::hash<int64_t>()(k.rows * 1315423911ll + k.chunks * 2654435761ll + k.rows_box * 97 +
-                              k.chunks_box * 13 + k.dtype);
+    h ^= std::hash<int64_t>()(k.rows * 1315423911ll + k.row_bytes * 40503ll +
+                              k.chunks * 2654435761ll + k.rows_box * 97 + k.chunks_box * 13 + k.dtype);
     return h;
   }
 };
 
-// Tensor map over a paged cache [rows = nb*bs][chunks*64 elems] viewed as
-// {64, rows, chunks} with strides {row_bytes, 128 B}; box {64, rows_box, chunks_box}.
-static int get_cache_map(const void* cache, int64_t rows, int chunks, int rows_box, int chunks_box,
-                         int dtype, CUtensorMap* out) {
+// Tensor map over a row-major 16-bit matrix [rows][>= chunks*64 elems] (row pitch row_bytes)
+// viewed as {64, rows, chunks} with strides {row_bytes, 128 B}; box {64, rows_box, chunks_box},
+// 128-byte swizzle: every box lands in shared memory as [chunk][row][128 B] SW128 panels.
+int get_panel_map(const void* cache, int64_t rows, int64_t row_bytes, int chunks, int rows_box,
+                  int chunks_box, int dtype, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache_maps;
-  MapKey key{cache, rows, chunks, rows_box, chunks_box, dtype};
+  MapKey key{cache, rows, row_bytes, chunks, rows_box, chunks_box, dtype};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache_maps.find(key);
   if (it != cache_maps.end()) {
@@ -505,7 +506,7 @@ static int get_cache_map(const void* cache, int64_t rows, int chunks, int rows_b
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return B200_ERR_DRIVER;
   cuuint64_t gdim[3] = {64, (cuuint64_t)rows, (cuuint64_t)chunks};
-  cuuint64_t gstride[2] = {(cuuint64_t)chunks * 128, 128};
+  cuuint64_t gstride[2] = {(cuuint64_t)row_bytes, 128};
   cuuint32_t box[3] = {64, (cuuint32_t)rows_box, (cuuint32_t)chunks_box};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
@@ -655,11 +656,11 @@ extern "C" int b200_paged_decode_attn(void* out, const void* q, const void* k_ca
   const int chunks = num_kv_heads * head_dim / 64;
   const int chunks_box = hkv_cta * head_dim / 64;
   CUtensorMap mk, mv;
-  int rc = get_cache_map(k_cache, (int64_t)num_blocks * block_size, chunks, p.rows_box, chunks_box,
-                         dtype, &mk);
+  int rc = get_panel_map(k_cache, (int64_t)num_blocks * block_size, (int64_t)chunks * 128, chunks,
+                         p.rows_box, chunks_box, dtype, &mk);
   if (rc != B200_OK) return rc;
-  rc = get_cache_map(v_cache, (int64_t)num_blocks * block_size, chunks, p.rows_box, chunks_box,
-                     dtype, &mv);
+  rc = get_panel_map(v_cache, (int64_t)num_blocks * block_size, (int64_t)chunks * 128, chunks,
+                     p.rows_box, chunks_box, dtype, &mv);
   if (rc != B200_OK) return rc;
 
   int grid = num_ctas > 0 ? num_ctas : num_sms();

@@ -4,13 +4,18 @@
 // flash_attn_varlen_func(causal=True[, block_table]) (layers/attention_ori.py:63-70) and the
 // oracle Attention._prefill_attn (layers/attention_torch_native.py:103-145).
 //
-// v1 (this file): 64x64 tiles, 4 warps x 16 query rows, K/V tiles double-buffered with
+// This file: the mma.sync variant (kept for strides TMA cannot describe and for A/B checks,
+// B200_PREFILL_KERNEL=mma_sync); the default is the tcgen05/TMEM kernel in prefill_umma.cu.
+// 64x64 tiles, 4 warps x 16 query rows, K/V tiles double-buffered with
 // cp.async into 128-byte-swizzled shared memory (same panel layout the TMA path uses), QK^T
 // and PV on mma.sync m16n8k16 with fp32 accumulation, fp32 online softmax in the exp2 domain,
 // bottom-right-aligned causal mask, K/V either packed [total_k, Hkv, D] or gathered from the
 // paged cache through block_tables (prefix-cache hit). Tensor-bound: 4*Lq*Lk*D flops per
 // (sequence, head) before causal halving.
 #include "common.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace b200 {
 
@@ -236,14 +241,30 @@ static int prefill_launch(const PrefillParams& p, int num_seqs, int max_seqlen_q
   return finish_launch();
 }
 
+int prefill_umma_launch(void* out, const void* q, const void* k, const void* v, const int32_t* cu_q,
+                        const int32_t* cu_k, int num_seqs, int total_q, int total_k,
+                        int max_seqlen_q, int H, int Hkv, int D, int64_t q_stride, int64_t k_stride,
+                        int64_t v_stride, int64_t out_stride, const int32_t* block_tables,
+                        int bt_stride, int num_blocks, int block_size, float scale, int dtype,
+                        cudaStream_t stream);  // prefill_umma.cu
+
+static bool use_umma() {
+  static int v = [] {
+    const char* e = getenv("B200_PREFILL_KERNEL");
+    return (e != nullptr && strcmp(e, "mma_sync") == 0) ? 0 : 1;
+  }();
+  return v != 0;
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" int b200_prefill_varlen_attn(void* out, const void* q, const void* k, const void* v,
                                         const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
-                                        int32_t num_seqs, int32_t max_seqlen_q,
-                                        int32_t max_seqlen_k, int32_t num_heads,
+                                        int32_t num_seqs, int32_t total_q, int32_t total_k,
+                                        int32_t max_seqlen_q, int32_t max_seqlen_k,
+                                        int32_t num_heads,
                                         int32_t num_kv_heads, int32_t head_dim, int64_t q_stride,
                                         int64_t k_stride, int64_t v_stride, int64_t out_stride,
                                         const int32_t* block_tables, int32_t block_table_stride,
@@ -271,6 +292,14 @@ extern "C" int b200_prefill_varlen_attn(void* out, const void* q, const void* k,
   B200_RETURN_IF(q_stride % 8 != 0 || out_stride % 2 != 0 || !aligned16(q) || !aligned16(k) ||
                      !aligned16(v) || (reinterpret_cast<uintptr_t>(out) & 3),
                  B200_ERR_MISALIGNED);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (use_umma()) {
+    const int rc = prefill_umma_launch(out, q, k, v, cu_seqlens_q, cu_seqlens_k, num_seqs, total_q,
+                                       total_k, max_seqlen_q, num_heads, num_kv_heads, head_dim,
+                                       q_stride, k_stride, v_stride, out_stride, block_tables,
+                                       block_table_stride, num_blocks, block_size, scale, dtype, s);
+    if (rc != B200_ERR_UNSUPPORTED) return rc;
+  }
   PrefillParams p;
   p.q = q, p.k = k, p.v = v, p.out = out;
   p.cu_q = cu_seqlens_q, p.cu_k = cu_seqlens_k;
@@ -279,7 +308,6 @@ extern "C" int b200_prefill_varlen_attn(void* out, const void* q, const void* k,
   p.H = num_heads, p.Hkv = num_kv_heads, p.G = num_heads / num_kv_heads;
   p.block_size = block_size, p.bt_stride = block_table_stride, p.num_blocks = num_blocks;
   p.scale_log2 = scale * 1.4426950408889634f;
-  cudaStream_t s = (cudaStream_t)stream;
   if (dtype == B200_DTYPE_BF16)
     return head_dim == 128 ? prefill_launch<__nv_bfloat16, 128>(p, num_seqs, max_seqlen_q, s)
                            : prefill_launch<__nv_bfloat16, 64>(p, num_seqs, max_seqlen_q, s);

@@ -36,7 +36,7 @@ PROTOTYPES = {
                                          c_size_t, c_int32, c_int32, c_void_p]),
     "b200_prefill_varlen_attn": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
-                                           c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                           c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                            c_int32, c_int32, c_int32, c_float, c_int32,
                                            c_void_p]),
     "b200_qknorm_rope_cache": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -174,6 +174,11 @@ class ModelRunner:
             peak, current = stats["allocated_bytes.all.peak"], stats["allocated_bytes.all.current"]
             available = total * cfg.gpu_memory_utilization - used - peak + current
             cfg.num_kvcache_blocks = int(available) // block_bytes
+        if self.world_size > 1:
+            # every rank must hold every block id the (rank-0) scheduler can hand out
+            n = torch.tensor([cfg.num_kvcache_blocks], dtype=torch.int64, device=self.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MIN)
+            cfg.num_kvcache_blocks = int(n.item())
         assert cfg.num_kvcache_blocks > 1, "not enough memory for the KV cache"
         self.kv_cache = torch.zeros(2, spec.num_layers, cfg.num_kvcache_blocks, self.block_size,
                                     kv_heads * spec.head_dim, dtype=self.dtype, device=self.device)

@@ -145,7 +145,8 @@ def prefill_varlen_attn(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_s
         bt_ptr, bt_stride = None, 0
     _C.check(_C.load().b200_prefill_varlen_attn(
         out.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), cu_seqlens_q.data_ptr(),
-        cu_seqlens_k.data_ptr(), num_seqs, int(max_seqlen_q), int(max_seqlen_k), H, num_kv_heads,
+        cu_seqlens_k.data_ptr(), num_seqs, Tq, 0 if block_tables is not None else k.shape[0],
+        int(max_seqlen_q), int(max_seqlen_k), H, num_kv_heads,
         D, q.stride(0) if Tq > 1 else H * D, ks, vs, out.stride(0) if Tq > 1 else H * D, bt_ptr,
         bt_stride, nb, bs, float(scale), _dt(q), _stream()), "b200_prefill_varlen_attn")
     return out
