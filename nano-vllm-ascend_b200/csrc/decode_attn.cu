@@ -87,6 +87,7 @@ paged_decode_kernel(const __grid_constant__ CUtensorMap tmK,
   uint64_t* empty = bars + 2 * kStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
 
   // ---- tiles per item -> exclusive prefix sum in shared memory
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
@@ -403,6 +404,7 @@ decode_combine_kernel(const DecodeParams p, int rows /* = HKV_CTA*G */) {
   constexpr int V = D / 32;  // columns per lane
   __shared__ float s_acc[4][D];
   __shared__ float s_ml[4][2];
+  pdl_wait();
   const int it = blockIdx.x, r = blockIdx.y;
   const int items = p.batch * p.hg_count;
   const int t0 = p.header[it], t1 = p.header[it + 1];
@@ -553,8 +555,9 @@ static int decode_launch_t(const CUtensorMap& mk, const CUtensorMap& mv, const D
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
-  decode_combine_kernel<T, D><<<dim3(items, HKV_CTA * p.G), 128, 0, stream>>>(p, HKV_CTA * p.G);
+  launch_pdl(kern, dim3(grid), dim3(kDecodeThreads), smem, stream, mk, mv, p);
+  launch_pdl(decode_combine_kernel<T, D>, dim3(items, HKV_CTA * p.G), dim3(128), 0, stream, p,
+             HKV_CTA * p.G);
   return finish_launch(2);
 }
 

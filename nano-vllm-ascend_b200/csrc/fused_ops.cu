@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256)
 rmsnorm_kernel(T* __restrict__ out, const T* __restrict__ x, T* __restrict__ residual,
                const T* __restrict__ weight, float eps, int hidden) {
   __shared__ float red[32];
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const int nvec = hidden / 8;
   const uint4* xrow = reinterpret_cast<const uint4*>(x + row * hidden);
@@ -116,12 +117,12 @@ static int rmsnorm_launch(void* out, const void* x, void* residual, const void* 
   if (threads < 128 && nvec >= 128) threads = 128;
   if (threads > 256) threads = 256;
   if (dtype == B200_DTYPE_BF16)
-    rmsnorm_kernel<__nv_bfloat16, kAdd><<<rows, threads, 0, stream>>>(
-        (__nv_bfloat16*)out, (const __nv_bfloat16*)x, (__nv_bfloat16*)residual,
-        (const __nv_bfloat16*)weight, eps, hidden);
+    launch_pdl(rmsnorm_kernel<__nv_bfloat16, kAdd>, dim3(rows), dim3(threads), 0, stream,
+               (__nv_bfloat16*)out, (const __nv_bfloat16*)x, (__nv_bfloat16*)residual,
+               (const __nv_bfloat16*)weight, eps, hidden);
   else
-    rmsnorm_kernel<__half, kAdd><<<rows, threads, 0, stream>>>(
-        (__half*)out, (const __half*)x, (__half*)residual, (const __half*)weight, eps, hidden);
+    launch_pdl(rmsnorm_kernel<__half, kAdd>, dim3(rows), dim3(threads), 0, stream, (__half*)out,
+               (const __half*)x, (__half*)residual, (const __half*)weight, eps, hidden);
   return finish_launch();
 }
 
@@ -130,6 +131,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 silu_and_mul_kernel(uint4* __restrict__ out, const uint4* __restrict__ x, int64_t rows,
                     int inter_vec) {
+  pdl_wait();
   const int64_t total = rows * inter_vec;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -153,9 +155,10 @@ silu_and_mul_kernel(uint4* __restrict__ out, const uint4* __restrict__ x, int64_
 }
 
 // ------------------------------------------------------------------ K8 qk-norm + RoPE + scatter
-// grid = (num_tokens, ceil((H + 2*Hkv) / 8)), 8 warps per CTA, one warp per head row.
-// Lane l owns elements {EPL*l .. EPL*l+EPL-1} of the first half and the same offsets in the
-// second half (EPL = D/64), i.e. exactly the (x1[i], x2[i]) pairs NeoX rotation couples.
+// One CTA (8 warps) per token and per group of 8*HPW head rows; LPH = D/16 lanes share a head row:
+// lane `sub` owns elements [8 sub, 8 sub + 8) of the first half and the same offsets of the
+// second half -- exactly the (x1[i], x2[i]) pairs the NeoX rotation couples -- so every access is
+// a 16-byte vector and a warp moves 4 (D=128) or 8 (D=64) head rows per pass.
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
 qknorm_rope_cache_kernel(T* __restrict__ qkv, const int64_t* __restrict__ positions,
@@ -164,17 +167,20 @@ qknorm_rope_cache_kernel(T* __restrict__ qkv, const int64_t* __restrict__ positi
                          T* __restrict__ v_cache, const int32_t* __restrict__ slots,
                          int slot_is_2d, int H, int Hkv, int64_t qkv_stride, int max_position,
                          int num_blocks, int block_size) {
-  constexpr int EPL = D / 64;  // elements per lane per half: 2 (D=128) or 1 (D=64)
   constexpr int HALF = D / 2;
+  constexpr int LPH = D / 16;     // lanes per head row
+  constexpr int HPW = 32 / LPH;   // head rows per warp
+  pdl_wait();
   const int token = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hidx = blockIdx.y * 8 + warp;
-  if (hidx >= H + 2 * Hkv) return;
-  T* row = qkv + (int64_t)token * qkv_stride + (int64_t)hidx * D;
+  const int sub = lane % LPH;
+  const int hidx = (blockIdx.y * 8 + warp) * HPW + lane / LPH;
+  const bool active = hidx < H + 2 * Hkv;
+  T* row = qkv + (int64_t)token * qkv_stride + (int64_t)(active ? hidx : 0) * D;
 
   // destination slot in the paged cache (k and v heads only)
   int64_t slot = -1;
-  if (hidx >= H && k_cache != nullptr) {
+  if (active && hidx >= H && k_cache != nullptr) {
     if (slot_is_2d) {
       const int blk = slots[2 * token], off = slots[2 * token + 1];
       if (blk >= 0 && blk < num_blocks && off >= 0 && off < block_size)
@@ -184,76 +190,84 @@ qknorm_rope_cache_kernel(T* __restrict__ qkv, const int64_t* __restrict__ positi
       if (s >= 0 && s < (int64_t)num_blocks * block_size) slot = s;
     }
   }
-
-  if (hidx >= H + Hkv) {  // ---- V head: plain copy into the cache
-    if (slot >= 0) {
-      const int vh = hidx - H - Hkv;
-      T* dst = v_cache + (slot * Hkv + vh) * D;
-      if (EPL == 2) {
-        reinterpret_cast<uint2*>(dst)[lane] = reinterpret_cast<const uint2*>(row)[lane];
-      } else {
-        reinterpret_cast<uint32_t*>(dst)[lane] = reinterpret_cast<const uint32_t*>(row)[lane];
-      }
-    }
-    return;
+  uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+  if (active) {
+    a = *reinterpret_cast<const uint4*>(row + 8 * sub);
+    b = *reinterpret_cast<const uint4*>(row + HALF + 8 * sub);
   }
-
+  const bool is_v = hidx >= H + Hkv;
+  if (active && is_v) {  // ---- V head: plain copy into the cache
+    if (slot >= 0) {
+      T* dst = v_cache + (slot * Hkv + (hidx - H - Hkv)) * D;
+      *reinterpret_cast<uint4*>(dst + 8 * sub) = a;
+      *reinterpret_cast<uint4*>(dst + HALF + 8 * sub) = b;
+    }
+  }
   const bool is_q = hidx < H;
   const T* w = is_q ? qw : kw;
-  float x1[EPL], x2[EPL];
-  if (EPL == 2) {
-    float2 a = unpack2<T>(reinterpret_cast<const uint32_t*>(row)[lane]);
-    float2 b = unpack2<T>(reinterpret_cast<const uint32_t*>(row + HALF)[lane]);
-    x1[0] = a.x, x1[EPL - 1] = a.y, x2[0] = b.x, x2[EPL - 1] = b.y;
-  } else {
-    x1[0] = to_f32<T>(row[lane]);
-    x2[0] = to_f32<T>(row[HALF + lane]);
-  }
-  if (w != nullptr) {  // per-head RMSNorm (layers/layernorm.py:16-25 applied to [T,H,D])
-    float ss = 0.f;
+  float x1[8], x2[8];
+  {
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) ss = fmaf(x1[i], x1[i], fmaf(x2[i], x2[i], ss));
-    ss = warp_sum(ss);
-    const float inv = rsqrt_exact(__fadd_rn(__fdiv_rn(ss, (float)D), eps));
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const float w1 = to_f32<T>(w[EPL * lane + i]), w2 = to_f32<T>(w[HALF + EPL * lane + i]);
-      const float n1 = to_f32<T>(from_f32<T>(__fmul_rn(x1[i], inv)));
-      const float n2 = to_f32<T>(from_f32<T>(__fmul_rn(x2[i], inv)));
-      x1[i] = to_f32<T>(from_f32<T>(__fmul_rn(n1, w1)));
-      x2[i] = to_f32<T>(from_f32<T>(__fmul_rn(n2, w2)));
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack2<T>(aw[j]), g = unpack2<T>(bw[j]);
+      x1[2 * j] = f.x, x1[2 * j + 1] = f.y, x2[2 * j] = g.x, x2[2 * j + 1] = g.y;
     }
   }
+  if (w != nullptr) {  // per-head RMSNorm (layers/layernorm.py:16-25 applied to [T,H,D]); warp-uniform
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss = fmaf(x1[i], x1[i], fmaf(x2[i], x2[i], ss));
+#pragma unroll
+    for (int o = 1; o < LPH; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = rsqrt_exact(__fadd_rn(__fdiv_rn(ss, (float)D), eps));
+    const uint4 wa = *reinterpret_cast<const uint4*>(w + 8 * sub);
+    const uint4 wb = *reinterpret_cast<const uint4*>(w + HALF + 8 * sub);
+    const uint32_t waw[4] = {wa.x, wa.y, wa.z, wa.w}, wbw[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 w1 = unpack2<T>(waw[j]), w2 = unpack2<T>(wbw[j]);
+      const float w1v[2] = {w1.x, w1.y}, w2v[2] = {w2.x, w2.y};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float n1 = to_f32<T>(from_f32<T>(__fmul_rn(x1[2 * j + e], inv)));
+        const float n2 = to_f32<T>(from_f32<T>(__fmul_rn(x2[2 * j + e], inv)));
+        x1[2 * j + e] = to_f32<T>(from_f32<T>(__fmul_rn(n1, w1v[e])));
+        x2[2 * j + e] = to_f32<T>(from_f32<T>(__fmul_rn(n2, w2v[e])));
+      }
+    }
+  }
+  if (!active || is_v) return;
   // NeoX rotation in fp32 (rotary_embedding.py:6-14): y1 = x1*cos - x2*sin, y2 = x2*cos + x1*sin
   int64_t pos = positions[token];
   if (pos < 0) pos = 0;
   if (pos >= max_position) pos = max_position - 1;
-  const float* cs = cos_sin + pos * D;
-  float y1[EPL], y2[EPL];
+  const float* cs = cos_sin + pos * D + 8 * sub;
+  const float4 c0 = *reinterpret_cast<const float4*>(cs), c1 = *reinterpret_cast<const float4*>(cs + 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(cs + HALF),
+               s1 = *reinterpret_cast<const float4*>(cs + HALF + 4);
+  const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  uint32_t o1[4], o2[4];
 #pragma unroll
-  for (int i = 0; i < EPL; ++i) {
-    const float c = cs[EPL * lane + i], s = cs[HALF + EPL * lane + i];
-    y1[i] = __fsub_rn(__fmul_rn(x1[i], c), __fmul_rn(x2[i], s));
-    y2[i] = __fadd_rn(__fmul_rn(x2[i], c), __fmul_rn(x1[i], s));
+  for (int j = 0; j < 4; ++j) {
+    float y1[2], y2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * j + e;
+      y1[e] = __fsub_rn(__fmul_rn(x1[i], cv[i]), __fmul_rn(x2[i], sv[i]));
+      y2[e] = __fadd_rn(__fmul_rn(x2[i], cv[i]), __fmul_rn(x1[i], sv[i]));
+    }
+    o1[j] = pack2<T>(y1[0], y1[1]);
+    o2[j] = pack2<T>(y2[0], y2[1]);
   }
-  T* kdst = nullptr;
-  if (!is_q && slot >= 0) kdst = k_cache + (slot * Hkv + (hidx - H)) * D;
-  if (EPL == 2) {
-    const uint32_t o1 = pack2<T>(y1[0], y1[EPL - 1]), o2 = pack2<T>(y2[0], y2[EPL - 1]);
-    reinterpret_cast<uint32_t*>(row)[lane] = o1;
-    reinterpret_cast<uint32_t*>(row + HALF)[lane] = o2;
-    if (kdst) {
-      reinterpret_cast<uint32_t*>(kdst)[lane] = o1;
-      reinterpret_cast<uint32_t*>(kdst + HALF)[lane] = o2;
-    }
-  } else {
-    const T o1 = from_f32<T>(y1[0]), o2 = from_f32<T>(y2[0]);
-    row[lane] = o1;
-    row[HALF + lane] = o2;
-    if (kdst) {
-      kdst[lane] = o1;
-      kdst[HALF + lane] = o2;
-    }
+  const uint4 r1 = make_uint4(o1[0], o1[1], o1[2], o1[3]), r2 = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  *reinterpret_cast<uint4*>(row + 8 * sub) = r1;
+  *reinterpret_cast<uint4*>(row + HALF + 8 * sub) = r2;
+  if (!is_q && slot >= 0) {
+    T* kdst = k_cache + (slot * Hkv + (hidx - H)) * D;
+    *reinterpret_cast<uint4*>(kdst + 8 * sub) = r1;
+    *reinterpret_cast<uint4*>(kdst + HALF + 8 * sub) = r2;
   }
 }
 
@@ -263,15 +277,16 @@ static int qknorm_launch(void* qkv, const int64_t* positions, const float* cos_s
                          const int32_t* slots, int slot_is_2d, int T_, int H, int Hkv, int D,
                          int64_t qkv_stride, int max_position, int num_blocks, int block_size,
                          cudaStream_t stream) {
-  dim3 grid(T_, (H + 2 * Hkv + 7) / 8);
+  const int rows_per_cta = 8 * (32 / (D / 16));
+  dim3 grid(T_, (H + 2 * Hkv + rows_per_cta - 1) / rows_per_cta);
   if (D == 128)
-    qknorm_rope_cache_kernel<T, 128><<<grid, 256, 0, stream>>>(
-        (T*)qkv, positions, cos_sin, (const T*)qw, (const T*)kw, eps, (T*)k_cache, (T*)v_cache,
-        slots, slot_is_2d, H, Hkv, qkv_stride, max_position, num_blocks, block_size);
+    launch_pdl(qknorm_rope_cache_kernel<T, 128>, grid, dim3(256), 0, stream, (T*)qkv, positions,
+               cos_sin, (const T*)qw, (const T*)kw, eps, (T*)k_cache, (T*)v_cache, slots, slot_is_2d,
+               H, Hkv, qkv_stride, max_position, num_blocks, block_size);
   else
-    qknorm_rope_cache_kernel<T, 64><<<grid, 256, 0, stream>>>(
-        (T*)qkv, positions, cos_sin, (const T*)qw, (const T*)kw, eps, (T*)k_cache, (T*)v_cache,
-        slots, slot_is_2d, H, Hkv, qkv_stride, max_position, num_blocks, block_size);
+    launch_pdl(qknorm_rope_cache_kernel<T, 64>, grid, dim3(256), 0, stream, (T*)qkv, positions,
+               cos_sin, (const T*)qw, (const T*)kw, eps, (T*)k_cache, (T*)v_cache, slots, slot_is_2d,
+               H, Hkv, qkv_stride, max_position, num_blocks, block_size);
   return finish_launch();
 }
 
@@ -282,8 +297,17 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
+// 32-bit finaliser (murmur3 fmix32): one draw per vocabulary entry
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
 
-// One CTA per row. score_i = logit_i / T + Gumbel_i (T given) or logit_i (greedy);
+// One CTA per row, 16-byte loads. score_i = logit_i / T + Gumbel_i (T > 0) or logit_i (greedy);
 // winner = argmax score, ties -> lowest index (torch.argmax semantics on a first-max basis).
 template <typename T>
 __global__ void __launch_bounds__(1024)
@@ -292,24 +316,39 @@ sample_kernel(int64_t* __restrict__ out, const T* __restrict__ logits,
               uint64_t step, const int64_t* __restrict__ step_offset) {
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
+  pdl_wait();
   const int row = blockIdx.x;
   const T* lrow = logits + (int64_t)row * stride;
   const float temp = temperatures == nullptr ? 0.f : temperatures[row];
   const bool greedy = !(temp > 0.f);   // no temperatures, or a non-positive one => argmax
   const float inv_t = greedy ? 1.f : 1.f / temp;
   if (step_offset != nullptr) step += (uint64_t)*step_offset;
-  const uint64_t key = splitmix64(seed ^ splitmix64(step * 0x100000001B3ull + row));
+  const uint64_t key64 = splitmix64(seed ^ splitmix64(step * 0x100000001B3ull + row));
+  const uint32_t key = (uint32_t)key64 ^ (uint32_t)(key64 >> 32);
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
-    float v = to_f32<T>(lrow[i]);
+  auto consider = [&](float v, int i) {
     if (!greedy) {
-      const uint64_t r = splitmix64(key + (uint64_t)i);
-      const float u = ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-      v = v * inv_t - __logf(-__logf(u));
+      const uint32_t r = mix32(key + (uint32_t)i * 0x9E3779B1u);
+      const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+      // Gumbel(0,1) = -ln(-ln u)
+      v = fmaf(v, inv_t, -0.6931471806f * __log2f(-0.6931471806f * __log2f(u)));
     }
     if (v > best || (v == best && i < best_i)) best = v, best_i = i;
+  };
+  const bool vec_ok = (stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int nvec = vec_ok ? vocab / 8 : 0;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    const uint4 q = ld_nc_v4(reinterpret_cast<const uint4*>(lrow) + vi);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack2<T>(w[j]);
+      consider(f.x, vi * 8 + 2 * j);
+      consider(f.y, vi * 8 + 2 * j + 1);
+    }
   }
+  for (int i = nvec * 8 + threadIdx.x; i < vocab; i += blockDim.x) consider(to_f32<T>(lrow[i]), i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -361,11 +400,11 @@ extern "C" int b200_silu_and_mul(void* out, const void* x, int32_t rows, int32_t
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   if (dtype == B200_DTYPE_BF16)
-    silu_and_mul_kernel<__nv_bfloat16>
-        <<<grid, 256, 0, (cudaStream_t)stream>>>((uint4*)out, (const uint4*)x, rows, inter / 8);
+    launch_pdl(silu_and_mul_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+               (uint4*)out, (const uint4*)x, (int64_t)rows, inter / 8);
   else
-    silu_and_mul_kernel<__half>
-        <<<grid, 256, 0, (cudaStream_t)stream>>>((uint4*)out, (const uint4*)x, rows, inter / 8);
+    launch_pdl(silu_and_mul_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+               (uint4*)out, (const uint4*)x, (int64_t)rows, inter / 8);
   return finish_launch();
 }
 
@@ -389,7 +428,8 @@ extern "C" int b200_qknorm_rope_cache(void* qkv, const int64_t* positions,
   B200_RETURN_IF(qkv_stride < (int64_t)(num_heads + 2 * num_kv_heads) * head_dim,
                  B200_ERR_BAD_SHAPE);
   B200_RETURN_IF(qkv_stride % 8 != 0 || !aligned16(qkv) || (k_cache && !aligned16(k_cache)) ||
-                     (v_cache && !aligned16(v_cache)),
+                     (v_cache && !aligned16(v_cache)) || !aligned16(cos_sin_cache) ||
+                     (q_norm_weight && (!aligned16(q_norm_weight) || !aligned16(k_norm_weight))),
                  B200_ERR_MISALIGNED);
   if (dtype == B200_DTYPE_BF16)
     return qknorm_launch<__nv_bfloat16>(qkv, positions, cos_sin_cache, q_norm_weight,
@@ -412,11 +452,11 @@ extern "C" int b200_sample(int64_t* out_tokens, const void* logits, const float*
   if (rows == 0) return B200_OK;
   B200_RETURN_IF(!out_tokens || !logits, B200_ERR_NULL_POINTER);
   if (dtype == B200_DTYPE_BF16)
-    sample_kernel<__nv_bfloat16><<<rows, 1024, 0, (cudaStream_t)stream>>>(
-        out_tokens, (const __nv_bfloat16*)logits, temperatures, vocab, logits_stride, seed, step,
-        step_offset);
+    launch_pdl(sample_kernel<__nv_bfloat16>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream,
+               out_tokens, (const __nv_bfloat16*)logits, temperatures, vocab, logits_stride, seed, step,
+               step_offset);
   else
-    sample_kernel<__half><<<rows, 1024, 0, (cudaStream_t)stream>>>(
-        out_tokens, (const __half*)logits, temperatures, vocab, logits_stride, seed, step, step_offset);
+    launch_pdl(sample_kernel<__half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, out_tokens,
+               (const __half*)logits, temperatures, vocab, logits_stride, seed, step, step_offset);
   return finish_launch();
 }

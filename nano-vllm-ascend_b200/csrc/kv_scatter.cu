@@ -18,6 +18,7 @@ kv_scatter_kernel(const uint4* __restrict__ key, const uint4* __restrict__ value
                   const int32_t* __restrict__ slots, int num_tokens, int vec_per_row,
                   int64_t key_stride_vec, int64_t value_stride_vec, int num_blocks,
                   int block_size) {
+  pdl_wait();
   const int64_t total = (int64_t)num_tokens * vec_per_row * 2;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -66,13 +67,13 @@ static int scatter_launch(const void* key, const void* value, void* k_cache, voi
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   if (slot2d)
-    kv_scatter_kernel<true><<<grid, 256, 0, stream>>>(
-        (const uint4*)key, (const uint4*)value, (uint4*)k_cache, (uint4*)v_cache, slots,
-        num_tokens, vec_per_row, key_stride / 8, value_stride / 8, num_blocks, block_size);
+    launch_pdl(kv_scatter_kernel<true>, dim3(grid), dim3(256), 0, stream, (const uint4*)key,
+               (const uint4*)value, (uint4*)k_cache, (uint4*)v_cache, slots, num_tokens, vec_per_row,
+               key_stride / 8, value_stride / 8, num_blocks, block_size);
   else
-    kv_scatter_kernel<false><<<grid, 256, 0, stream>>>(
-        (const uint4*)key, (const uint4*)value, (uint4*)k_cache, (uint4*)v_cache, slots,
-        num_tokens, vec_per_row, key_stride / 8, value_stride / 8, num_blocks, block_size);
+    launch_pdl(kv_scatter_kernel<false>, dim3(grid), dim3(256), 0, stream, (const uint4*)key,
+               (const uint4*)value, (uint4*)k_cache, (uint4*)v_cache, slots, num_tokens, vec_per_row,
+               key_stride / 8, value_stride / 8, num_blocks, block_size);
   return finish_launch();
 }
 

@@ -52,6 +52,7 @@ prefill_attn_kernel(const PrefillParams p) {
   uint8_t* sq = smem;
   uint8_t* sk = smem + TILE_BYTES;       // [2][TILE_BYTES]
   uint8_t* sv = smem + 3 * TILE_BYTES;   // [2][TILE_BYTES]
+  pdl_wait();
 
   const int seq = blockIdx.z, head = blockIdx.y;
   const int q0 = p.cu_q[seq], Lq = p.cu_q[seq + 1] - q0;
@@ -237,7 +238,7 @@ static int prefill_launch(const PrefillParams& p, int num_seqs, int max_seqlen_q
     attr_set = true;
   }
   dim3 grid((max_seqlen_q + kBM - 1) / kBM, p.H, num_seqs);
-  kern<<<grid, kPrefillThreads, smem, stream>>>(p);
+  launch_pdl(kern, grid, dim3(kPrefillThreads), smem, stream, p);
   return finish_launch();
 }
 

@@ -8,8 +8,10 @@
 // CTA = one (sequence, head, 256 query rows): two 128-row query tiles t = 0, 1.
 //   warps 0-3 / 4-7   softmax warpgroup of tile t: one thread per query row (= one TMEM lane);
 //                     reads S from TMEM, fp32 online softmax (exp2 domain), rescales O in TMEM
-//                     when the row max moves, writes P (bf16) as a K-major SW128 smem panel
-//   warp 8            TMA producer: Q tiles once, then a 3-stage ring of 64-key K and V tiles
+//                     only when the row max grew by > 2^8 (lazy rescale), writes P (bf16) as a
+//                     K-major SW128 smem panel (double-buffered)
+//   warp 8            TMA producers: lane 0 loads Q then runs a 3-stage K ring, lane 1 a 3-stage V ring
+//                     (64-key tiles; K stages recycle after S(j), V stages after PV(j))
 //   warp 9            MMA issuer (one lane):  S[t] = Q[t] K^T   (M128 N64 K16 x D/16)
 //                                             O[t] += P[t] V    (M128 N=D K16 x 4, V MN-major)
 // TMEM (512 columns, one CTA per SM):  O[t] at 128 t,  S[t][buf] at 256 + 128 t + 64 buf.
@@ -50,17 +52,19 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;                            // [2][QTILE]
   uint8_t* sK = sQ + 2 * QTILE;                  // [kUStages][KTILE]
   uint8_t* sV = sK + kUStages * KTILE;           // [kUStages][KTILE]
-  uint8_t* sP = sV + kUStages * KTILE;           // [2][PTILE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PTILE);
+  uint8_t* sP = sV + kUStages * KTILE;           // [2 tiles][2 buffers][PTILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * PTILE);
   uint64_t* q_full = bars;                       // [1]
   uint64_t* k_full = bars + 1;                   // [kUStages]
   uint64_t* v_full = k_full + kUStages;          // [kUStages]
-  uint64_t* kv_empty = v_full + kUStages;        // [kUStages]
-  uint64_t* s_full = kv_empty + kUStages;        // [2 tiles][2 buffers]
+  uint64_t* k_empty = v_full + kUStages;         // [kUStages] K stage consumed by S(j) MMAs
+  uint64_t* v_empty = k_empty + kUStages;        // [kUStages] V stage consumed by PV(j) MMAs
+  uint64_t* s_full = v_empty + kUStages;         // [2 tiles][2 buffers]
   uint64_t* p_full = s_full + 4;                 // [2]
-  uint64_t* o_full = p_full + 2;                 // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* o_full = p_full + 2;                 // [2 tiles][2 P buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
+  pdl_wait();
   const int seq = blockIdx.z, head = blockIdx.y;
   const int q0 = p.cu_q[seq], Lq = p.cu_q[seq + 1] - q0;
   const int k0 = p.cu_k[seq], Lk = p.cu_k[seq + 1] - k0;
@@ -85,13 +89,12 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int s = 0; s < kUStages; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&p_full[t], kUBM);
-      mbar_init(&o_full[t], 1);
-    }
+    for (int t = 0; t < 2; ++t) mbar_init(&p_full[t], kUBM);
+    for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
     mbar_fence_init();
   }
   if (warp == 9) umma::tmem_alloc(tmem_slot, 512);
@@ -102,31 +105,38 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 8) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      uint64_t pol_keep, pol_stream = l2_policy_evict_first();
+    // lane 0: Q once, then the K ring; lane 1: the V ring. K stages are released as soon as the
+    // S MMAs that read them retire (one iteration before the matching PV), V stages after PV,
+    // so each ring keeps ~3 tiles of lead over its consumer instead of one.
+    if (lane < 2) {
+      const bool is_k = lane == 0;
+      const CUtensorMap* tm = is_k ? &tmK : &tmV;
+      tma_prefetch_desc(tm);
+      uint64_t pol_keep;
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      mbar_expect_tx(q_full, ntq * QTILE);
-      for (int t = 0; t < ntq; ++t)
-        tma_load_3d(sQ + t * QTILE, &tmQ, q_full, 0, q0 + m0 + t * kUBM, head * CH, pol_stream);
+      if (is_k) {
+        tma_prefetch_desc(&tmQ);
+        const uint64_t pol_stream = l2_policy_evict_first();
+        mbar_expect_tx(q_full, ntq * QTILE);
+        for (int t = 0; t < ntq; ++t)
+          tma_load_3d(sQ + t * QTILE, &tmQ, q_full, 0, q0 + m0 + t * kUBM, head * CH, pol_stream);
+      }
+      uint8_t* ring = is_k ? sK : sV;
+      uint64_t* full = is_k ? k_full : v_full;
+      uint64_t* empty = is_k ? k_empty : v_empty;
       for (int j = 0; j < NT; ++j) {
         const int s = j % kUStages;
-        mbar_wait(&kv_empty[s], ((j / kUStages) & 1) ^ 1);
+        mbar_wait(&empty[s], ((j / kUStages) & 1) ^ 1);
         const int n0 = j * kUBN;
         if (p.block_tables == nullptr) {
-          mbar_expect_tx(&k_full[s], KTILE);
-          tma_load_3d(sK + s * KTILE, &tmK, &k_full[s], 0, k0 + n0, kvh * CH, pol_keep);
-          mbar_expect_tx(&v_full[s], KTILE);
-          tma_load_3d(sV + s * KTILE, &tmV, &v_full[s], 0, k0 + n0, kvh * CH, pol_keep);
+          mbar_expect_tx(&full[s], KTILE);
+          tma_load_3d(ring + s * KTILE, tm, &full[s], 0, k0 + n0, kvh * CH, pol_keep);
         } else {
           const int rb = p.kv_rows_box;
           const int nops = min(kUBN / rb, (Lk - n0 + rb - 1) / rb);
           const int per_op = p.kv_split ? CH : 1;
           const int op_bytes = rb * 128 * (p.kv_split ? 1 : CH);
-          mbar_expect_tx(&k_full[s], nops * per_op * op_bytes);
-          mbar_expect_tx(&v_full[s], nops * per_op * op_bytes);
+          mbar_expect_tx(&full[s], nops * per_op * op_bytes);
           for (int o = 0; o < nops; ++o) {
             const int tok = n0 + o * rb;
             const int entry = tok / p.block_size;
@@ -134,8 +144,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int row = blk < 0 ? -(1 << 30) : blk * p.block_size + (tok - entry * p.block_size);
             for (int c = 0; c < per_op; ++c) {
               const int dst = (p.kv_split ? c * KPANEL : 0) + o * rb * 128;
-              tma_load_3d(sK + s * KTILE + dst, &tmK, &k_full[s], 0, row, kvh * CH + c, pol_keep);
-              tma_load_3d(sV + s * KTILE + dst, &tmV, &v_full[s], 0, row, kvh * CH + c, pol_keep);
+              tma_load_3d(ring + s * KTILE + dst, tm, &full[s], 0, row, kvh * CH + c, pol_keep);
             }
           }
         }
@@ -143,53 +152,65 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 9) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc_s = umma::make_idesc<T>(kUBM, kUBN, 0, 0);   // S = Q K^T, both K-major
-      const uint32_t idesc_o = umma::make_idesc<T>(kUBM, D, 0, 1);      // O = P V, V MN-major
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV),
-                     p_addr = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const int s = j % kUStages;
-        mbar_wait(&k_full[s], (j / kUStages) & 1);
-        umma::fence_after_sync();
+    // The whole warp walks the loop (warp-uniform control flow and descriptor arithmetic, so it
+    // lives on the uniform datapath); one elected lane issues. Descriptors are loop-invariant
+    // bases + compile-time offsets: issuing an MMA costs a couple of integer adds, which matters
+    // because a 128x64x16 MMA retires in 32 cycles.
+    const uint32_t idesc_s = umma::make_idesc<T>(kUBM, kUBN, 0, 0);   // S = Q K^T, both K-major
+    const uint32_t idesc_o = umma::make_idesc<T>(kUBM, D, 0, 1);      // O = P V, V MN-major
+    const uint64_t qd0 = umma::desc_kmajor(smem_u32(sQ));
+    const uint64_t kd0 = umma::desc_kmajor(smem_u32(sK));
+    const uint64_t vd0 = umma::desc_mnmajor(smem_u32(sV), KPANEL);
+    const uint64_t pd0 = umma::desc_kmajor(smem_u32(sP));
+    const bool leader = umma::elect_one();
+    auto issue_s = [&](int j) {
+      const int s = j % kUStages;
+      mbar_wait(&k_full[s], (j / kUStages) & 1);
+      umma::fence_after_sync();
+      const uint64_t kd = umma::desc_advance(kd0, s * KTILE);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (j < n_tiles[t]) {
-            const uint32_t d = tb + 256 + t * 128 + (j & 1) * 64;
+      for (int t = 0; t < 2; ++t) {
+        if (j < n_tiles[t]) {
+          const uint32_t d = tb + 256 + t * 128 + (j & 1) * 64;
+          if (leader) {
 #pragma unroll
             for (int ks = 0; ks < D / 16; ++ks) {
-              const uint32_t koff = (ks >> 2) * 1 /*panel*/;
-              const uint64_t ad = umma::desc_kmajor(q_addr + t * QTILE + koff * QPANEL + (ks & 3) * 32);
-              const uint64_t bd = umma::desc_kmajor(k_addr + s * KTILE + koff * KPANEL + (ks & 3) * 32);
+              const uint64_t ad = umma::desc_advance(qd0, t * QTILE + (ks >> 2) * QPANEL + (ks & 3) * 32);
+              const uint64_t bd = umma::desc_advance(kd, (ks >> 2) * KPANEL + (ks & 3) * 32);
               umma::mma_ss(d, ad, bd, idesc_s, ks > 0);
             }
             umma::commit(&s_full[t * 2 + (j & 1)]);
           }
         }
-      };
-      mbar_wait(q_full, 0);
-      umma::fence_after_sync();
-      if (NT > 0) issue_s(0);
-      for (int j = 0; j < NT; ++j) {
-        if (j + 1 < NT) issue_s(j + 1);
-        const int s = j % kUStages;
-        mbar_wait(&v_full[s], (j / kUStages) & 1);
+      }
+      if (leader) umma::commit(&k_empty[s]);     // K stage free once these S MMAs have retired
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    umma::fence_after_sync();
+    if (NT > 0) issue_s(0);
+    for (int j = 0; j < NT; ++j) {
+      if (j + 1 < NT) issue_s(j + 1);
+      const int s = j % kUStages;
+      mbar_wait(&v_full[s], (j / kUStages) & 1);
+      const uint64_t vd = umma::desc_advance(vd0, s * KTILE);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (j < n_tiles[t]) {
-            mbar_wait(&p_full[t], j & 1);
-            umma::fence_after_sync();
+      for (int t = 0; t < 2; ++t) {
+        if (j < n_tiles[t]) {
+          mbar_wait(&p_full[t], j & 1);
+          umma::fence_after_sync();
+          if (leader) {
+            const uint64_t pd = umma::desc_advance(pd0, (t * 2 + (j & 1)) * PTILE);
 #pragma unroll
-            for (int kk = 0; kk < kUBN / 16; ++kk) {
-              const uint64_t ad = umma::desc_kmajor(p_addr + t * PTILE + kk * 32);
-              const uint64_t bd = umma::desc_mnmajor(v_addr + s * KTILE + kk * 16 * 128, KPANEL);
-              umma::mma_ss(tb + t * 128, ad, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-            }
-            umma::commit(&o_full[t]);
+            for (int kk = 0; kk < kUBN / 16; ++kk)
+              umma::mma_ss(tb + t * 128, umma::desc_advance(pd, kk * 32),
+                           umma::desc_advance(vd, kk * 16 * 128), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            umma::commit(&o_full[t * 2 + (j & 1)]);
           }
         }
-        umma::commit(&kv_empty[s]);
       }
+      if (leader) umma::commit(&v_empty[s]);
+      __syncwarp();
     }
   } else {
     // =========================== softmax warpgroups ===========================
@@ -199,8 +220,12 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int qrow = m0 + t * kUBM + row;            // row inside the sequence
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float sl2 = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + t * PTILE;
+    // m_ref is the max the accumulators are currently expressed against. It only follows the true
+    // running max when that moved by more than 2^kLazy (exp2 domain): P values stay < 2^kLazy,
+    // harmless for fp32 accumulation / bf16 P, and the expensive TMEM round trip that rescales O
+    // becomes rare after the first tiles.
+    constexpr float kLazy = 8.f;
+    float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
       umma::fence_after_sync();
@@ -224,22 +249,13 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float mx = sv[0];
 #pragma unroll
       for (int c = 1; c < 64; ++c) mx = fmaxf(mx, sv[c]);
-      const float m_new = fmaxf(m_run, mx);
-      const float mb = m_new == -INFINITY ? 0.f : m_new * sl2;
-      const float alpha = m_new == -INFINITY ? 1.f : ex2_approx((m_run - m_new) * sl2);
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        sv[c] = ex2_approx(fmaf(sv[c], sl2, -mb));
-        sum += sv[c];
-      }
-      l_run = fmaf(l_run, alpha, sum);
-      m_run = m_new;
-      if (j > 0) {
-        // PV(j-1) must have finished before O is rescaled and before P is overwritten
-        mbar_wait(&o_full[t], (j - 1) & 1);
-        umma::fence_after_sync();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+      const bool grow = (mx - m_ref) * sl2 > kLazy;       // also true for the first finite max
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m_ref;
+        const float alpha = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - m_new) * sl2);
+        if (j > 0) {
+          mbar_wait(&o_full[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);   // PV(j-1) landed
+          umma::fence_after_sync();
 #pragma unroll
           for (int c0 = 0; c0 < D; c0 += 32) {
             uint32_t orr[32];
@@ -251,8 +267,20 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           umma::wait_st();
         }
+        l_run *= alpha;
+        m_ref = m_new;
       }
-      // P row -> smem (K-major SW128 panel: 64 keys = 128 bytes per row)
+      const float mb = m_ref == -INFINITY ? 0.f : m_ref * sl2;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        sv[c] = ex2_approx(fmaf(sv[c], sl2, -mb));
+        sum += sv[c];
+      }
+      l_run += sum;
+      // P(j) goes to buffer j&1, last read by PV(j-2)
+      if (j >= 2) mbar_wait(&o_full[t * 2 + (j & 1)], ((j >> 1) - 1) & 1);
+      uint8_t* prow = sP + (t * 2 + (j & 1)) * PTILE;
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16) {
         uint4 v;
@@ -270,7 +298,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (m0 + t * kUBM < Lq) {
       T* orow = reinterpret_cast<T*>(p.out) + (int64_t)(q0 + qrow) * p.out_stride + (int64_t)head * D;
       if (nt > 0) {
-        mbar_wait(&o_full[t], (nt - 1) & 1);
+        mbar_wait(&o_full[t * 2 + ((nt - 1) & 1)], ((nt - 1) >> 1) & 1);
         umma::fence_after_sync();
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
 #pragma unroll
@@ -306,7 +334,7 @@ static int prefill_umma_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, c
                                  cudaStream_t stream) {
   constexpr int CH = D / 64;
   constexpr size_t smem = 1024 + 2 * CH * kUBM * 128 + 2 * kUStages * CH * kUBN * 128 +
-                          2 * kUBM * 128 + 32 * 8 + 16;
+                          4 * kUBM * 128 + 32 * 8 + 16;
   auto kern = prefill_umma_kernel<T, D>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -315,7 +343,7 @@ static int prefill_umma_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, c
     attr_set = true;
   }
   dim3 grid((max_seqlen_q + 2 * kUBM - 1) / (2 * kUBM), p.H, num_seqs);
-  kern<<<grid, kUThreads, smem, stream>>>(mq, mk, mv, p);
+  launch_pdl(kern, grid, dim3(kUThreads), smem, stream, mq, mk, mv, p);
   return finish_launch();
 }
 

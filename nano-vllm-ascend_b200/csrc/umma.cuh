@@ -127,6 +127,22 @@ __device__ __forceinline__ void wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor + byte offset of the start address (the 14-bit address field never carries: all
+// shared memory addresses are < 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
+  return desc + (uint64_t)(bytes >> 4);
+}
+
 // byte offset of (row, 16-byte chunk c16 in [0,8)) inside one SW128 panel
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t c16) {
   return row * 128u + ((c16 ^ (row & 7u)) << 4);

@@ -204,20 +204,27 @@ class ModelRunner:
         for seq in seqs:
             n = len(seq)
             start = min(seq.num_cached_tokens, n - 1) if hit else 0
-            ids.extend(seq[start:])
-            pos.extend(range(start, n))
+            ids.append(np.asarray(seq.token_ids[start:] if start else seq.token_ids, dtype=np.int64))
+            t = np.arange(start, n, dtype=np.int64)
+            pos.append(t)
             cu_q.append(cu_q[-1] + n - start)
             cu_k.append(cu_k[-1] + n)
             max_q, max_k = max(max_q, n - start), max(max_k, n)
             if seq.block_table:
-                for t in range(start, n):
-                    slots.append(seq.block_table[t // bs] * bs + t % bs)
+                table = np.asarray(seq.block_table, dtype=np.int64)
+                slots.append(table[t // bs] * bs + t % bs)
+        ids = np.concatenate(ids) if ids else np.zeros(0, np.int64)
+        pos = np.concatenate(pos) if pos else np.zeros(0, np.int64)
+        slots = np.concatenate(slots).astype(np.int32) if slots else None
         dev = self.device
         block_tables = self._dense_block_tables(seqs) if any(s.block_table for s in seqs) else None
-        as_dev = lambda data, dt: torch.tensor(data, dtype=dt, pin_memory=True).to(dev, non_blocking=True)
+
+        def as_dev(data, dt):
+            host = torch.from_numpy(data) if isinstance(data, np.ndarray) else torch.tensor(data, dtype=dt)
+            return host.to(dt).pin_memory().to(dev, non_blocking=True)
         set_context(True, cu_seqlens_q=as_dev(cu_q, torch.int32), cu_seqlens_k=as_dev(cu_k, torch.int32),
                     max_seqlen_q=max_q, max_seqlen_k=max_k,
-                    slot_mapping=as_dev(slots, torch.int32) if slots else None,
+                    slot_mapping=as_dev(slots, torch.int32) if slots is not None else None,
                     context_lens=None, block_tables=block_tables, is_enforce_eager=True,
                     real_bs=len(seqs), block_size=bs, paged_prefill=hit)
         return as_dev(ids, torch.int64), as_dev(pos, torch.int64)

@@ -87,7 +87,7 @@ def decode_workspace(batch, num_heads, num_kv_heads, head_dim, device) -> torch.
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     ws = _decode_ws.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)   # arrival counters start at 0
         _decode_ws[key] = ws
     return ws
 

@@ -28,15 +28,26 @@ def _engine(model, **kw):
     return LLM(model, **kw)
 
 
-def _greedy(llm, prompts, max_tokens, capture=None):
+def _greedy(llm, prompts, max_tokens, capture=None, force_tokens=None, picked=None):
+    """capture: list receiving each step's logits; force_tokens[step] (list per sequence): teacher
+    forcing -- the engine continues with these ids whatever its own argmax (kept in `picked`) was,
+    so every step stays comparable with a reference run even across a near-tie."""
     from nanovllm import SamplingParams
     runner = llm.model_runner
-    if capture is not None:
+    if capture is not None or force_tokens is not None:
         orig = runner.sampler.forward
+        step = [0]
 
         def spy(logits, *a, **k):
-            capture.append(logits.float().cpu())
-            return orig(logits, *a, **k)
+            if capture is not None:
+                capture.append(logits.float().cpu())
+            out = orig(logits, *a, **k)
+            if picked is not None:
+                picked.append(out.cpu().tolist())
+            if force_tokens is not None and step[0] < len(force_tokens):
+                out.copy_(torch.tensor(force_tokens[step[0]], dtype=out.dtype, device=out.device))
+            step[0] += 1
+            return out
         runner.sampler.forward = spy
     outs = llm.generate(prompts, SamplingParams(temperature=1.0, max_tokens=max_tokens, ignore_eos=True,
                                                 greedy=True), use_tqdm=False)
@@ -59,8 +70,9 @@ def test_qwen3_0_6b_config1_greedy_matches_reference(golden_models):
     """BASELINE config 1 on the GPU: random-init Qwen3-0.6B, 1 prompt, block 16, 32 tokens."""
     g = golden_models["qwen3_0_6b_config1"]
     llm = _engine("qwen3-0.6b", seed=g["seed"], enforce_eager=True, max_num_seqs=4)
-    logs = []
-    toks = _greedy(llm, g["prompts"], g["max_tokens"], capture=logs)
+    logs, picked = [], []
+    forced = [[t] for t in g["tokens"][0]]       # teacher-force the reference ids (one sequence)
+    _greedy(llm, g["prompts"], g["max_tokens"], capture=logs, force_tokens=forced, picked=picked)
     llm.exit()
     got = torch.stack(logs)[:, 0]                # [32, vocab]
     ref_top = g["top_values"]
@@ -70,11 +82,12 @@ def test_qwen3_0_6b_config1_greedy_matches_reference(golden_models):
     margin = (ref_top[:, 0] - ref_top[:, 1])
     decided = margin > 2 * err                   # steps where the reference itself is unambiguous
     assert decided.float().mean() > 0.8
-    for t in range(len(toks[0])):
+    for t in range(len(picked)):
         if decided[t]:
-            assert toks[0][t] == g["tokens"][0][t], t
+            assert picked[t][0] == g["tokens"][0][t], t
         else:                                    # near tie: must still pick one of the tied leaders
-            assert toks[0][t] in g["top_indices"][t, :2].tolist(), t
+            tied = g["top_indices"][t][ref_top[t] >= ref_top[t, 0] - 2 * err].tolist()
+            assert picked[t][0] in tied, (t, picked[t][0], tied)
     assert (got.mean(-1) - g["logit_mean"]).abs().max() < 5e-3
     assert (got.std(-1) - g["logit_std"]).abs().max() < 5e-3
 

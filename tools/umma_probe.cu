@@ -69,3 +69,48 @@ extern "C" int umma_probe(const void* A, const void* B, float* out, int N, int K
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const bf16*)A, (const bf16*)B, out, N, K, mode);
   return (int)cudaGetLastError();
 }
+
+// ---- throughput probe: one CTA per SM issues `reps` x (ksteps MMAs) back to back and reports the
+// cycles per MMA instruction for a given shape / operand majorness.
+extern "C" __global__ void __launch_bounds__(128)
+umma_rate_kernel(long long* cycles_out, int N, int ksteps, int b_mn, int reps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma::make_idesc<bf16>(128, N, 0, b_mn);
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem) + 32 * 1024;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ad = umma::desc_kmajor(a_addr + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
+        const uint64_t bd = b_mn ? umma::desc_mnmajor(b_addr + (ks & 3) * 16 * 128, 64 * 128)
+                                 : umma::desc_kmajor(b_addr + (ks >> 2) * (N * 128) + (ks & 3) * 32);
+        umma::mma_ss(tb + (r & 1) * 256, ad, bd, idesc, ks > 0);
+      }
+    }
+    umma::commit(&bar);
+    mbar_wait(&bar, 0);
+    cycles_out[blockIdx.x] = clock64() - t0;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, 512);
+}
+
+extern "C" int umma_rate(long long* cycles_out, int blocks, int N, int ksteps, int b_mn, int reps, void* stream) {
+  size_t smem = 1024 + 96 * 1024;
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  umma_rate_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(cycles_out, N, ksteps, b_mn, reps);
+  return (int)cudaGetLastError();
+}
