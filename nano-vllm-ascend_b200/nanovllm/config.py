@@ -42,11 +42,16 @@ def preset_hf_config(name: str):
                         num_attention_heads=4, num_key_value_heads=2, head_dim=64,
                         intermediate_size=256, rms_norm_eps=1e-6, max_position_embeddings=512,
                         tie_word_embeddings=True, attention_bias=False, rope_theta=1000000.0)
+    elif key == "tiny-llama":
+        c = LlamaConfig(vocab_size=512, hidden_size=256, num_hidden_layers=2,
+                        num_attention_heads=4, num_key_value_heads=2, head_dim=64,
+                        intermediate_size=512, rms_norm_eps=1e-5, max_position_embeddings=512,
+                        tie_word_embeddings=True, rope_theta=10000.0)
     else:
         return None
     c.architectures = ["LlamaForCausalLM" if "llama" in key else "Qwen3ForCausalLM"]
     c.dtype = "bfloat16"
-    c.eos_token_id = -1 if key == "tiny-qwen3" else c.eos_token_id
+    c.eos_token_id = -1 if key.startswith("tiny-") else c.eos_token_id
     return c
 
 

@@ -156,3 +156,89 @@ def test_temperature_sampling_runs_and_varies():
     seqs = [tuple(o["token_ids"]) for o in outs]
     assert all(len(s) == 16 for s in seqs)
     assert len(set(seqs)) > 1      # identical prompts, hot temperature: rows must not all coincide
+
+
+def test_llama_family_matches_oracle():
+    """LlamaForCausalLM path (no QK-norm, per-layer rope tables, explicit scale) against the oracle's
+    evaluation of the same graph (models/llama.py semantics), teacher-forced on the oracle's ids."""
+    rnd = random.Random(21)
+    prompts = [[rnd.randint(0, 511) for _ in range(n)] for n in (13, 70)]
+    cfg = M.ModelCfg(vocab_size=512, hidden_size=256, num_layers=2, num_heads=4, num_kv_heads=2,
+                     head_dim=64, intermediate_size=512, rms_eps=1e-5, rope_theta=10000.0,
+                     max_position=512, qk_norm=False)
+    w = M.seeded_weights(cfg, seed=9, norm_jitter=0.1)
+    tr = M.generate_greedy(w, cfg, prompts, 10, 16, attn_mode="exact")
+    forced = [[tr.tokens[i][t] for i in range(2)] for t in range(10)]
+    llm = _engine("tiny-llama", seed=9, norm_jitter=0.1, enforce_eager=True)
+    logs = []
+    _greedy(llm, prompts, 10, capture=logs, force_tokens=forced)
+    llm.exit()
+    got, want = torch.stack(logs), torch.stack(tr.logits)
+    diff = (got - want).abs()
+    assert diff.max() < 0.06 and diff.pow(2).mean().sqrt() < 0.01, (diff.max(), diff.pow(2).mean().sqrt())
+
+
+def test_drop_in_layers_unfused_path():
+    """The reference operator surface used the reference way (no fused K8): RMSNorm modules on
+    [T,H,D] views, get_rope(...)(positions, q, k), Attention.forward(q, k, v) doing its own KV
+    scatter -- prefill then one decode step -- against the oracle."""
+    from nanovllm.layers.attention import Attention
+    from nanovllm.layers.layernorm import RMSNorm
+    from nanovllm.layers.rotary_embedding import get_rope
+    from nanovllm.utils.context import reset_context, set_context
+    from oracle import attention_ref as A
+    from oracle import layers_ref as L
+    H, G, D, bs, nb = 8, 2, 128, 16, 12
+    g = torch.Generator().manual_seed(4)
+    bf = torch.bfloat16
+    lens = [20, 37]
+    T = sum(lens)
+    q = torch.randn(T, H, D, generator=g).to(bf)
+    k = torch.randn(T, G, D, generator=g).to(bf)
+    v = torch.randn(T, G, D, generator=g).to(bf)
+    wq = (1 + 0.1 * torch.randn(D, generator=g)).to(bf)
+    pos = torch.cat([torch.arange(n) for n in lens])
+    tables = [[3, 7], [1, 9, 4]]
+    slots = torch.cat([torch.tensor([tables[i][t // bs] * bs + t % bs for t in range(n)])
+                       for i, n in enumerate(lens)]).to(torch.int32)
+    cu = torch.tensor([0, 20, 57], dtype=torch.int32)
+    # oracle
+    cache = L.rope_cache(D, 256, 10000.0)
+    qn = L.apply_rope(pos, L.rmsnorm(q, wq, 1e-6), cache)
+    kn = L.apply_rope(pos, L.rmsnorm(k, wq, 1e-6), cache)
+    kc = torch.zeros(nb, bs, G, D, dtype=bf)
+    vc = torch.zeros_like(kc)
+    A.store_kvcache(kn, v, kc, vc, slots, bs)
+    want = A.prefill_attention(qn, kn, v, cu, cu, G, D, mode="exact", scale=D ** -0.5)
+    # product modules
+    with torch.device("cuda"):
+        norm = RMSNorm(D, 1e-6)
+        attn = Attention(H, D, None, G)
+        rope = get_rope(D, D, 256, 10000.0)
+    norm.weight.data = wq.cuda()
+    attn.k_cache = torch.zeros(nb, bs, G * D, dtype=bf, device="cuda")
+    attn.v_cache = torch.zeros_like(attn.k_cache)
+    qd, kd = norm(q.cuda()), norm(k.cuda())
+    qd, kd = rope(pos.cuda(), qd, kd)
+    set_context(True, cu_seqlens_q=cu.cuda(), cu_seqlens_k=cu.cuda(), max_seqlen_q=37, max_seqlen_k=37,
+                slot_mapping=slots.cuda(), block_tables=None, block_size=bs)
+    got = attn(qd, kd, v.cuda())
+    assert got.shape == (T, H * D)
+    assert (got.cpu().float() - want).abs().max() < 2e-2
+    assert (attn.k_cache.cpu().view(nb, bs, G, D).float() - kc.float()).abs().max() < 2e-2
+    # one decode step for both sequences, 2-D (block, offset) slots as the reference runner builds them
+    qs = torch.randn(2, H, D, generator=g).to(bf)
+    ks = torch.randn(2, G, D, generator=g).to(bf)
+    vs = torch.randn(2, G, D, generator=g).to(bf)
+    new_len = [21, 38]
+    slot2 = torch.tensor([[tables[i][(n - 1) // bs], (n - 1) % bs] for i, n in enumerate(new_len)], dtype=torch.int32)
+    flat = (slot2[:, 0] * bs + slot2[:, 1]).to(torch.int32)
+    A.store_kvcache(ks, vs, kc, vc, flat, bs)
+    bt = torch.tensor([[3, 7, -1], [1, 9, 4]], dtype=torch.int32)
+    ctx = torch.tensor(new_len, dtype=torch.int32)
+    want_d = A.decode_attention(qs, kc, vc, ctx, bt, G, D, mode="exact", scale=D ** -0.5)
+    set_context(False, slot_mapping=slot2.cuda(), context_lens=ctx.cuda(), block_tables=bt.cuda(),
+                is_enforce_eager=True, real_bs=2, block_size=bs)
+    got_d = attn(qs.cuda().view(2, -1), ks.cuda().view(2, -1), vs.cuda().view(2, -1))   # 2-D inputs allowed
+    reset_context()
+    assert (got_d.cpu().float() - want_d).abs().max() < 2e-2

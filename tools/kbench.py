@@ -61,6 +61,25 @@ def bench_prefill(nseq, L, H, G, D):
                 TFLOPs_med=round(flops / med / 1e9, 1), TFLOPs_best=round(flops / best / 1e9, 1))
 
 
+def bench_prefill_prefix_hit(qlen, klen, H, G, D, bs):
+    """Config-3 form: a prompt whose first klen-qlen tokens hit the prefix cache: q_len << k_len,
+    K/V read from the paged cache through block_tables (attention_ori.py:65-66)."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nblk = (klen + bs - 1) // bs
+    kc = torch.randn(nblk + 1, bs, G * D, device="cuda", generator=g).to(torch.bfloat16)
+    vc = torch.randn(nblk + 1, bs, G * D, device="cuda", generator=g).to(torch.bfloat16)
+    q = torch.randn(qlen, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    bt = torch.randperm(nblk, device="cuda", generator=g).to(torch.int32).view(1, -1).contiguous()
+    cu_q = torch.tensor([0, qlen], dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor([0, klen], dtype=torch.int32, device="cuda")
+    out = torch.empty(qlen, H * D, dtype=torch.bfloat16, device="cuda")
+    fn = lambda: ops.prefill_varlen_attn(q, kc, vc, cu_q, cu_k, qlen, klen, D ** -0.5, G, block_tables=bt, out=out)
+    med, best = timeit(fn, iters=10, warmup=3)
+    flops = 4 * H * D * (qlen * (klen - qlen) + qlen * qlen / 2)
+    return dict(kernel="prefill_prefix_hit", qlen=qlen, klen=klen, H=H, G=G, D=D, bs=bs, ms_med=round(med, 4),
+                TFLOPs_med=round(flops / med / 1e9, 1))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -77,5 +96,6 @@ if __name__ == "__main__":
     if args.what in ("prefill", "all"):
         res.append(bench_prefill(16, 1024, 16, 8, 128))
         res.append(bench_prefill(1, 8192, 32, 8, 64))
+        res.append(bench_prefill_prefix_hit(256, 8192, 32, 8, 64, 16))
     for r in res:
         print(json.dumps(r))

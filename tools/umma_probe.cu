@@ -87,21 +87,31 @@ umma_rate_kernel(long long* cycles_out, int N, int ksteps, int b_mn, int reps) {
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
-  if (threadIdx.x == 0) {
+  if (warp == 1) {
+    // warp-uniform loop, precomputed descriptors, one elected lane issues (as the real kernel does)
     const uint32_t idesc = umma::make_idesc<bf16>(128, N, 0, b_mn);
     const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem) + 32 * 1024;
+    uint64_t ad[8], bd[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      ad[ks] = umma::desc_kmajor(a_addr + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
+      bd[ks] = b_mn ? umma::desc_mnmajor(b_addr + (ks & 3) * 16 * 128, 64 * 128)
+                    : umma::desc_kmajor(b_addr + (ks >> 2) * (N * 128) + (ks & 3) * 32);
+    }
+    const bool leader = umma::elect_one();
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t ad = umma::desc_kmajor(a_addr + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
-        const uint64_t bd = b_mn ? umma::desc_mnmajor(b_addr + (ks & 3) * 16 * 128, 64 * 128)
-                                 : umma::desc_kmajor(b_addr + (ks >> 2) * (N * 128) + (ks & 3) * 32);
-        umma::mma_ss(tb + (r & 1) * 256, ad, bd, idesc, ks > 0);
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          if (ks < ksteps) umma::mma_ss(tb + (r & 1) * 256, ad[ks], bd[ks], idesc, ks > 0);
       }
+      __syncwarp();
     }
-    umma::commit(&bar);
+    if (leader) umma::commit(&bar);
+    __syncwarp();
     mbar_wait(&bar, 0);
-    cycles_out[blockIdx.x] = clock64() - t0;
+    if (leader) cycles_out[blockIdx.x] = clock64() - t0;
   }
   umma::fence_before_sync();
   __syncthreads();
