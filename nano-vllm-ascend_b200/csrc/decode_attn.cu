@@ -394,63 +394,81 @@ paged_decode_kernel(const __grid_constant__ CUtensorMap tmK,
   }
 }
 
-// Combine kernel: one CTA per (item = sequence x head group, output row); merges the partial
-// results of items whose tiles were split across CTAs. Items handled by a single CTA were
-// written directly: exit. Each of the 4 warps folds a strided subset of the partials with
-// coalesced row loads (lane = D/32 consecutive columns), then warp 0 folds the 4 warps.
+// Combine kernel: merges the partial results of items whose tiles were split across CTAs.
+// One CTA per range boundary c | c+1: the item that straddles that boundary is merged by the
+// FIRST boundary it straddles (every other block exits at once), so the grid is #CTAs-1 blocks
+// instead of one block per (item, row). gridDim.y == 1 (large batches, few pieces per item):
+// the 8 warps take the rows round-robin and fold the pieces serially. gridDim.y == rows (small
+// batches, one item cut into up to #CTAs pieces): block (c, r) folds row r, its 8 warps split
+// the pieces and meet in shared memory. Lane = D/32 consecutive columns in both modes.
 template <typename T, int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 decode_combine_kernel(const DecodeParams p, int rows /* = HKV_CTA*G */) {
-  constexpr int V = D / 32;  // columns per lane
-  __shared__ float s_acc[4][D];
-  __shared__ float s_ml[4][2];
+  constexpr int V = D / 32;
+  __shared__ float s_acc[8][D];
+  __shared__ float s_ml[8][2];
   pdl_wait();
-  const int it = blockIdx.x, r = blockIdx.y;
   const int items = p.batch * p.hg_count;
-  const int t0 = p.header[it], t1 = p.header[it + 1];
-  const int per = p.header[items + 1];
-  if (t1 == t0) return;
-  const int c_first = t0 / per, c_last = (t1 - 1) / per;
-  if (c_first == c_last) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float m = -INFINITY, l = 0.f, acc[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) acc[i] = 0.f;
-  for (int c = c_first + warp; c <= c_last; c += 4) {
-    const int slot = 2 * c + ((c * per >= t0) ? 0 : 1);
-    const float* ml = p.part_ml + ((int64_t)slot * rows + r) * 2;
-    const float* po = p.part_o + ((int64_t)slot * rows + r) * D + lane * V;
-    const float mc = ml[0], lc = ml[1];
-    const float m_new = fmaxf(m, mc);
-    const float a = ex2_approx(m - m_new), b = ex2_approx(mc - m_new);
-    l = l * a + lc * b;
-#pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = acc[i] * a + po[i] * b;
-    m = m_new;
+  const int per = p.header[items + 1], total = p.header[items + 2];
+  const int c = blockIdx.x;
+  const int tb = (c + 1) * per;                 // first tile of range c+1
+  if (tb >= total) return;
+  int lo = 0, hi = items;                       // item holding tile tb
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.header[mid] <= tb) lo = mid; else hi = mid;
   }
+  const int it = lo, t0 = p.header[it], t1 = p.header[it + 1];
+  if (t0 == tb) return;                         // item starts exactly here: not cut at this boundary
+  const int c_first = t0 / per, c_last = (t1 - 1) / per;
+  if (c_first != c) return;                     // an earlier boundary owns this item
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = it / p.hg_count, hg = it - b * p.hg_count;
+  T* obase = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_stride + (int64_t)hg * rows * D;
+  const bool by_rows = gridDim.y == 1;
+  const int r_begin = by_rows ? warp : (int)blockIdx.y;
+  const int r_step = by_rows ? 8 : rows;        // second mode: exactly one row per block
+  for (int r = r_begin; r < rows; r += r_step) {
+    float m = -INFINITY, l = 0.f, acc[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) s_acc[warp][lane * V + i] = acc[i];
-  if (lane == 0) s_ml[warp][0] = m, s_ml[warp][1] = l;
-  __syncthreads();
-  if (warp == 0) {
-    float M = fmaxf(fmaxf(s_ml[0][0], s_ml[1][0]), fmaxf(s_ml[2][0], s_ml[3][0]));
-    float L = 0.f, o[V];
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int cc = c_first + (by_rows ? 0 : warp); cc <= c_last; cc += (by_rows ? 1 : 8)) {
+      const int slot = 2 * cc + ((cc * per >= t0) ? 0 : 1);
+      const float* ml = p.part_ml + ((int64_t)slot * rows + r) * 2;
+      const float* po = p.part_o + ((int64_t)slot * rows + r) * D + lane * V;
+      const float mc = ml[0], lc = ml[1];
+      const float m_new = fmaxf(m, mc);
+      const float a = ex2_approx(m - m_new), bsc = ex2_approx(mc - m_new);
+      l = l * a + lc * bsc;
 #pragma unroll
-    for (int i = 0; i < V; ++i) o[i] = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float sc = ex2_approx(s_ml[w][0] - M);  // exp2(-inf) == 0 for idle warps
-      L = fmaf(s_ml[w][1], sc, L);
-#pragma unroll
-      for (int i = 0; i < V; ++i) o[i] = fmaf(s_acc[w][lane * V + i], sc, o[i]);
+      for (int i = 0; i < V; ++i) acc[i] = acc[i] * a + po[i] * bsc;
+      m = m_new;
     }
-    const float inv = 1.f / L;
-    const int b = it / p.hg_count, hg = it - b * p.hg_count;
-    T* orow = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_stride + ((int64_t)hg * rows + r) * D +
-              lane * V;
+    if (!by_rows) {                             // fold the 8 warps' shares of this row
+#pragma unroll
+      for (int i = 0; i < V; ++i) s_acc[warp][lane * V + i] = acc[i];
+      if (lane == 0) s_ml[warp][0] = m, s_ml[warp][1] = l;
+      __syncthreads();
+      if (warp != 0) return;
+      m = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, s_ml[w][0]);
+      l = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float sc = ex2_approx(s_ml[w][0] - m);   // exp2(-inf) == 0 for idle warps
+        l = fmaf(s_ml[w][1], sc, l);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = fmaf(s_acc[w][lane * V + i], sc, acc[i]);
+      }
+    }
+    const float inv = 1.f / l;
+    T* orow = obase + (int64_t)r * D + lane * V;
 #pragma unroll
     for (int i = 0; i < V; i += 2)
-      *reinterpret_cast<uint32_t*>(orow + i) = pack2<T>(o[i] * inv, o[i + 1] * inv);
+      *reinterpret_cast<uint32_t*>(orow + i) = pack2<T>(acc[i] * inv, acc[i + 1] * inv);
   }
 }
 
@@ -556,9 +574,14 @@ static int decode_launch_t(const CUtensorMap& mk, const CUtensorMap& mv, const D
     attr_set = true;
   }
   launch_pdl(kern, dim3(grid), dim3(kDecodeThreads), smem, stream, mk, mv, p);
-  launch_pdl(decode_combine_kernel<T, D>, dim3(items, HKV_CTA * p.G), dim3(128), 0, stream, p,
-             HKV_CTA * p.G);
-  return finish_launch(2);
+  if (grid > 1) {
+    // large batches: items are cut into 2-3 pieces -> one block per boundary handles all rows;
+    // small batches: one item may span every CTA -> one block per (boundary, row)
+    const int rows = HKV_CTA * p.G;
+    const dim3 cgrid(grid - 1, items >= 64 ? 1 : rows);
+    launch_pdl(decode_combine_kernel<T, D>, cgrid, dim3(256), 0, stream, p, rows);
+  }
+  return finish_launch(grid > 1 ? 2 : 1);
 }
 
 template <typename T, int D>

@@ -239,6 +239,20 @@ def test_decode_ragged(H, G, D, bs):
         assert torch.count_nonzero(o[9]) == 0          # context_len == 0 row -> zeros
 
 
+def test_decode_many_sequences_ragged():
+    """>= 64 sequences (the one-block-per-boundary combine mode), ragged lengths incl. one sequence
+    far longer than the per-CTA share, several persistent grid sizes."""
+    g = torch.Generator().manual_seed(77)
+    lens = torch.randint(1, 300, (96,), generator=g).tolist()
+    lens[5], lens[40], lens[41] = 3000, 0, 1
+    q, kc, vc, ctx, bt = _decode_case(len(lens), 16, 8, 128, 16, lens, seed=123)
+    want = A.decode_attention(q, kc, vc, ctx, bt, 8, 128, mode="exact", scale=128 ** -0.5)
+    for ctas in (0, 7, 148, 300):
+        o = _run_decode(q, kc, vc, ctx, bt, 8, 128, num_ctas=ctas)
+        assert (o.float() - want).abs().max() < 2e-2, ctas
+        assert torch.count_nonzero(o[40]) == 0
+
+
 def test_decode_fp16_and_stale_nan_rows():
     """fp16 caches; stale rows past the context hold NaN bit patterns and must not leak."""
     lens = [5, 40, 77]
