@@ -193,6 +193,34 @@ int b200_sample(int64_t* out_tokens, const void* logits, const float* temperatur
                 uint64_t step, const int64_t* step_offset, int32_t dtype,
                 b200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------
+ * C1 (fused)  tensor-parallel all-reduce + residual add + RMSNorm in one kernel over NVLink peer
+ * memory, for decode-sized messages.
+ * Replaces: dist.all_reduce(y) in RowParallelLinear.forward            layers/linear.py:151-152
+ *           followed by RMSNorm.add_rms_forward                        layers/layernorm.py:27-38
+ *           (call chain models/qwen3.py:89,118 -> :155-159).
+ * Every rank's row-parallel GEMM writes its partial [rows, hidden] into a buffer mapped by all
+ * ranks (b200_comm_* below). peer_bufs[r] / peer_flags[r] (HOST arrays of `world` device
+ * pointers) are rank r's partial buffer and flag array (>= 8 uint32, zero-initialised) as
+ * addressable from this rank; `state` is a local zero-initialised uint32[4]. All ranks must issue
+ * the same sequence of calls; consecutive calls must alternate between two partial buffers.
+ * Result: residual <- cast(sum_r partial_r) + residual ; out <- RMSNorm(that sum) * weight, with
+ * the rounding points of the reference (sum materialised in dtype, add in fp32).
+ * ------------------------------------------------------------------------------- */
+int b200_allreduce_add_rmsnorm(void* out, void* residual, const void* weight, float eps,
+                               int32_t rows, int32_t hidden, const void* const* peer_bufs,
+                               void* const* peer_flags, void* state, int32_t world, int32_t rank,
+                               int32_t dtype, b200_stream_t stream);
+
+/* Set-up helpers for the peer buffers (NOT hot path: they allocate / map memory, synchronously).
+ * alloc: cudaMalloc + zero; get/open_handle: CUDA IPC (64-byte handle, peer access enabled
+ * lazily); all return 0 or a cudaError_t value. */
+int b200_comm_alloc(size_t bytes, void** ptr);
+int b200_comm_free(void* ptr);
+int b200_comm_get_handle(const void* ptr, void* handle64);
+int b200_comm_open_handle(const void* handle64, void** ptr);
+int b200_comm_close_handle(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

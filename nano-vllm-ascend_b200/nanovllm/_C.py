@@ -48,6 +48,14 @@ PROTOTYPES = {
     "b200_add_rmsnorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,
                                    c_int32, c_void_p]),
     "b200_silu_and_mul": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "b200_allreduce_add_rmsnorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,
+                                             c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                             c_void_p]),
+    "b200_comm_alloc": (c_int32, [c_size_t, c_void_p]),
+    "b200_comm_free": (c_int32, [c_void_p]),
+    "b200_comm_get_handle": (c_int32, [c_void_p, c_void_p]),
+    "b200_comm_open_handle": (c_int32, [c_void_p, c_void_p]),
+    "b200_comm_close_handle": (c_int32, [c_void_p]),
     "b200_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_uint64,
                               c_uint64, c_void_p, c_int32, c_void_p]),
 }

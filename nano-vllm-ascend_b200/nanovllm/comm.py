@@ -1,0 +1,104 @@
+"""Peer-memory communicator for the fused tensor-parallel all-reduce (C1).
+
+One cudaMalloc'd region per rank, mapped into every other rank with CUDA IPC (NVLink P2P):
+  [ partial buffer 0 | partial buffer 1 | flags (uint32[8]) | state (uint32[4]) ]
+The row-parallel GEMMs write their partial products straight into partial buffer `parity`; the
+fused kernel (b200_allreduce_add_rmsnorm) reads every rank's copy. Set-up uses
+torch.distributed only to exchange the 64-byte IPC handles.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _C
+
+
+class _RawCudaBuffer:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class PeerAllReduce:
+    FLAG_BYTES = 256
+
+    def __init__(self, device: torch.device, max_bytes: int = 4 << 20):
+        lib = _C.load()
+        self.lib = lib
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device
+        self.max_bytes = int(max_bytes)
+        total = 2 * self.max_bytes + 2 * self.FLAG_BYTES
+        ptr = ctypes.c_void_p()
+        _C.check(lib.b200_comm_alloc(total, ctypes.byref(ptr)), "b200_comm_alloc")
+        self.local_ptr = ptr.value
+        handle = ctypes.create_string_buffer(64)
+        _C.check(lib.b200_comm_get_handle(self.local_ptr, handle), "b200_comm_get_handle")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.peer_ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.peer_ptrs.append(self.local_ptr)
+            else:
+                p = ctypes.c_void_p()
+                _C.check(lib.b200_comm_open_handle(handles[r], ctypes.byref(p)), "b200_comm_open_handle")
+                self.peer_ptrs.append(p.value)
+        self.local = torch.as_tensor(_RawCudaBuffer(self.local_ptr, total), device=device)
+        arr = ctypes.c_void_p * self.world
+        self._bufs = [arr(*[p + par * self.max_bytes for p in self.peer_ptrs]) for par in (0, 1)]
+        self._flags = arr(*[p + 2 * self.max_bytes for p in self.peer_ptrs])
+        self._state = self.local_ptr + 2 * self.max_bytes + self.FLAG_BYTES
+        self._parity = 0
+        self.pending = None          # (tensor, parity) written by the last deferred row-parallel GEMM
+        dist.barrier()
+
+    def fits(self, rows: int, hidden: int, itemsize: int) -> bool:
+        return rows * hidden * itemsize <= self.max_bytes and hidden % 8 == 0 and hidden <= 8192
+
+    def partial_buffer(self, rows: int, hidden: int, dtype: torch.dtype) -> torch.Tensor:
+        """View of this rank's next partial buffer; the GEMM writes its output here."""
+        parity = self._parity
+        self._parity ^= 1
+        n = rows * hidden * dtype.itemsize
+        view = self.local[parity * self.max_bytes:parity * self.max_bytes + n].view(dtype).view(rows, hidden)
+        self.pending = (view, parity)
+        return view
+
+    def allreduce_add_rmsnorm(self, out, residual, weight, eps):
+        """out <- RMSNorm(sum_r partial_r + residual) * weight; residual updated in place.
+        `out` may be any [rows, hidden] tensor (normally a fresh one; the partial buffer itself must
+        not be used: peers may still be reading it)."""
+        view, parity = self.pending
+        self.pending = None
+        rows, hidden = view.shape
+        from .ops import _dt, _stream
+        _C.check(self.lib.b200_allreduce_add_rmsnorm(
+            out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
+            self._bufs[parity], self._flags, self._state, self.world, self.rank, _dt(view), _stream()),
+            "b200_allreduce_add_rmsnorm")
+        return out, residual
+
+    def close(self):
+        for r, p in enumerate(self.peer_ptrs):
+            if r != self.rank:
+                self.lib.b200_comm_close_handle(p)
+        self.local = None
+        self.lib.b200_comm_free(self.local_ptr)
+
+
+_ACTIVE: PeerAllReduce | None = None
+
+
+def get_comm() -> PeerAllReduce | None:
+    return _ACTIVE
+
+
+def set_comm(comm: PeerAllReduce | None) -> None:
+    global _ACTIVE
+    _ACTIVE = comm

@@ -90,6 +90,11 @@ class ModelRunner:
             seeded_init(self.model, seed=config.seed, norm_jitter=config.norm_jitter)
         self.model.eval()
         self.spec = self.model.spec
+        self.comm = None
+        if self.world_size > 1 and os.environ.get("B200_PEER_ALLREDUCE", "1") != "0":
+            from ..comm import PeerAllReduce, set_comm
+            self.comm = PeerAllReduce(self.device)
+            set_comm(self.comm)
         self.sampler = Sampler(seed=config.seed)
 
         self._warmup_prefill()
@@ -138,6 +143,14 @@ class ModelRunner:
 
     def exit(self):
         self.graphs.clear()
+        if self.comm is not None:
+            from ..comm import set_comm
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier()
+            set_comm(None)
+            self.comm.close()
+            self.comm = None
         if self.world_size > 1 and not self.spmd:
             self.shm.close()
             dist.barrier()

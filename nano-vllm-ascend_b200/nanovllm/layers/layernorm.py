@@ -23,4 +23,10 @@ class RMSNorm(nn.Module):
     def forward(self, x: torch.Tensor, residual: torch.Tensor | None = None):
         if residual is None:
             return ops.rmsnorm(x.contiguous(), self.weight, self.eps)
+        from ..comm import get_comm
+        comm = get_comm()
+        if comm is not None and comm.pending is not None and comm.pending[0] is x:
+            # x is this rank's PARTIAL row-parallel output sitting in the peer-mapped buffer:
+            # all-reduce + residual add + norm in one kernel over NVLink (C1 fused)
+            return comm.allreduce_add_rmsnorm(torch.empty_like(x), residual, self.weight, self.eps)
         return ops.add_rmsnorm_(x, residual, self.weight, self.eps)

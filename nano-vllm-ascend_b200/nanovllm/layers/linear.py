@@ -121,6 +121,9 @@ class RowParallelLinear(LinearBase):
     def __init__(self, input_size, output_size, bias=False):
         _, tp = tp_rank_size()
         super().__init__(divide(input_size, tp), output_size, bias, 1)
+        # set by decoder stacks whose next op is a residual-add RMSNorm: the all-reduce is then
+        # deferred and fused into that norm over NVLink peer memory (comm.py) for small messages
+        self.defer_allreduce = False
 
     def weight_loader(self, param, loaded_weight):
         if param.dim() <= self.tp_dim:          # bias: replicated, applied on rank 0 only
@@ -130,7 +133,18 @@ class RowParallelLinear(LinearBase):
         param.data.copy_(loaded_weight.narrow(self.tp_dim, self.tp_rank * n, n))
 
     def forward(self, x):
-        y = F.linear(x, self.weight, self.bias if self.tp_rank == 0 else None)
+        bias = self.bias if self.tp_rank == 0 else None
+        if self.tp_size > 1 and self.defer_allreduce and x.dim() == 2:
+            from ..comm import get_comm
+            comm = get_comm()
+            if comm is not None and comm.fits(x.shape[0], self.weight.shape[0], x.dtype.itemsize):
+                buf = comm.partial_buffer(x.shape[0], self.weight.shape[0], x.dtype)
+                if bias is None:
+                    torch.mm(x, self.weight.t(), out=buf)
+                else:
+                    torch.addmm(bias, x, self.weight.t(), out=buf)
+                return buf          # partial sum; RMSNorm(x, residual) completes the all-reduce
+        y = F.linear(x, self.weight, bias)
         if self.tp_size > 1:
             dist.all_reduce(y)
         return y

@@ -119,6 +119,10 @@ class DecoderLayer(nn.Module):
         self.mlp = DecoderMLP(spec)
         self.input_layernorm = RMSNorm(spec.hidden_size, eps=spec.rms_eps)
         self.post_attention_layernorm = RMSNorm(spec.hidden_size, eps=spec.rms_eps)
+        # both row-parallel outputs of a layer feed a residual-add RMSNorm (post_attention_layernorm,
+        # then the next layer's input_layernorm / the final norm): their all-reduce may be fused there
+        self.self_attn.o_proj.defer_allreduce = True
+        self.mlp.down_proj.defer_allreduce = True
 
     def forward(self, positions, hidden_states, residual):
         if residual is None:
