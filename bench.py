@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--block-size", type=int, default=16)
     ap.add_argument("--tp", action="store_true", help="tensor-parallel over --gpus instead of replicas")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mem-util", type=float, default=0.7, help="gpu_memory_utilization of the engine")
     ap.add_argument("--cpu-sample-seqs", type=int, default=32)
     return ap.parse_args()
 
@@ -204,7 +205,7 @@ def main():
     llm = LLM(args.model, kvcache_block_size=args.block_size, max_num_seqs=B,
               max_model_len=max(4096, max_len), max_num_batched_tokens=16384,
               tensor_parallel_size=world if args.tp else 1, distributed_launch="env",
-              gpu_memory_utilization=0.7, seed=0)
+              gpu_memory_utilization=args.mem_util, seed=0)
     runner = llm.model_runner
     spec = runner.spec
     rnd = random.Random(rank if not args.tp else 0)
@@ -330,7 +331,7 @@ def main():
                      "step_frac_of_kv_roofline": (B * K / dev_s) / (B / (step_kv_bytes / (peak * 1e9)))},
         "clocks": clk,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "qwen3-0.6b":
         tps, sec = cpu_reference_step(args.cpu_sample_seqs, ctx, args.block_size, 3, 1)
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{args.cpu_sample_seqs} of {B} sequences, one full 28-layer decode "

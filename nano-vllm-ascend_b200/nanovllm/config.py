@@ -76,6 +76,8 @@ class Config:
     # additions (all optional; defaults keep the reference behaviour)
     seed: int = 0                      # random-init / sampler seed
     norm_jitter: float = 0.0           # random-init only
+    init_device: str = "auto"          # random-init: "cpu" (name-seeded, == oracle), "cuda", or "auto"
+                                       # (cuda above 2e9 parameters)
     load_weights: bool | None = None   # None: load iff *.safetensors exist under `model`
     distributed_launch: str = "spawn"  # "spawn": reference style (rank 0 spawns workers);
                                        # "env": every rank is already running (torchrun/SPMD)

@@ -28,7 +28,7 @@ from ..config import Config, GraphMode
 from ..layers.sampler import Sampler
 from ..models.models_map import model_dict
 from ..utils.context import get_context, reset_context, set_context
-from ..utils.loader import load_model, seeded_init
+from ..utils.loader import device_init, load_model, seeded_init
 from .sequence import Sequence
 
 _SHM_NAME = "nano_vllm_b200"
@@ -87,7 +87,12 @@ class ModelRunner:
         if config.load_weights if config.load_weights is not None else has_ckpt:
             load_model(self.model, config.model)
         else:
-            seeded_init(self.model, seed=config.seed, norm_jitter=config.norm_jitter)
+            n_params = sum(p.numel() for p in self.model.parameters())
+            on_device = config.init_device == "cuda" or (config.init_device == "auto" and n_params > 2e9)
+            if on_device:
+                device_init(self.model, seed=config.seed)
+            else:
+                seeded_init(self.model, seed=config.seed, norm_jitter=config.norm_jitter)
         self.model.eval()
         self.spec = self.model.spec
         self.comm = None

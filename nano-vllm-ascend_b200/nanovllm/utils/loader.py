@@ -47,6 +47,25 @@ def full_shapes(model: nn.Module, tp_size: int) -> dict[str, tuple[int, ...]]:
     return shapes
 
 
+def device_init(model: nn.Module, seed: int = 0, std: float = 0.02) -> None:
+    """Random init generated ON the device (for models too large to draw on the host in reasonable
+    time, e.g. Qwen3-32B = 65 GB): same distribution as seeded_init, not the same numbers; each
+    rank of a tensor-parallel group seeds by (seed, rank), which is fine for throughput runs."""
+    from ..layers.linear import tp_rank_size
+    rank, _ = tp_rank_size()
+    tied = getattr(getattr(model, "spec", None), "tie_embeddings", False)
+    for idx, (name, p) in enumerate(sorted(model.named_parameters())):
+        if tied and name == "lm_head.weight":
+            continue
+        gen = torch.Generator(device=p.device).manual_seed(seed * 1000003 + idx * 17 + rank)
+        if p.dim() == 1:
+            p.data.fill_(1.0)
+        else:
+            p.data.normal_(0.0, std, generator=gen)
+    if tied:
+        model.lm_head.weight.data = model.model.embed_tokens.weight.data
+
+
 def seeded_init(model: nn.Module, seed: int = 0, norm_jitter: float = 0.0, std: float = 0.02) -> None:
     """Deterministic random init keyed by parameter NAME (identical to oracle/model_ref.py's
     ``seeded_weights``): the i-th name in sorted order draws from Generator(seed*1000003 + i);
