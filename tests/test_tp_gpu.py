@@ -34,3 +34,57 @@ def test_tp2_matches_tp1(enforce_eager):
     # the sharded sums are reassociated (two partial products + all-reduce), so a token may only
     # differ where the logits nearly tie; the tiny model's margins are >= 0.1, far above that
     assert got == want
+
+
+def _ar_worker(rank, world, port, out_q):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (ROOT, os.path.join(ROOT, "nano-vllm-ascend_b200")):
+        sys.path.insert(0, p)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+    from nanovllm.comm import PeerAllReduce
+    from oracle import layers_ref as L
+    comm = PeerAllReduce(torch.device("cuda", rank))
+    ok = True
+    for it, (rows, hidden) in enumerate([(256, 1024), (1, 1024), (37, 5120), (256, 128), (5, 1024), (8, 2048)]):
+        g = torch.Generator().manual_seed(100 + it)                  # same stream on every rank
+        parts = [torch.randn(rows, hidden, generator=g).bfloat16() for _ in range(world)]
+        res = torch.randn(rows, hidden, generator=g).bfloat16()
+        w = (1 + 0.1 * torch.randn(hidden, generator=g)).bfloat16()
+        total = torch.stack([p.float() for p in parts]).sum(0).bfloat16()   # all-reduce result in bf16
+        want, want_res = L.add_rmsnorm(total, res, w, 1e-6)
+        assert comm.fits(rows, hidden, 2)
+        buf = comm.partial_buffer(rows, hidden, torch.bfloat16)
+        buf.copy_(parts[rank].cuda())
+        res_d = res.cuda()
+        out = torch.empty(rows, hidden, dtype=torch.bfloat16, device="cuda")
+        comm.allreduce_add_rmsnorm(out, res_d, w.cuda(), 1e-6)
+        torch.cuda.synchronize()
+        d_out = (out.cpu().float() - want.float()).abs().max().item()
+        d_res = (res_d.cpu().float() - want_res.float()).abs().max().item()
+        # fp32 sum order differs from torch's stacked sum by <= 1 bf16 ulp of |x| ~ 4
+        ok = ok and d_out < 0.07 and d_res < 0.07
+    dist.barrier()
+    comm.close()
+    out_q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_fused_peer_allreduce_add_rmsnorm_kernel():
+    """b200_allreduce_add_rmsnorm on 2 GPUs (CUDA IPC peer buffers over NVLink) against
+    all-reduce (sum materialised in bf16) followed by the reference's add_rms_forward."""
+    _need_gpus(2)
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ar_worker, args=(r, 2, 28031, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: True, 1: True}
