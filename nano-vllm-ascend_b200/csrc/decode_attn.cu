@@ -43,6 +43,7 @@ struct DecodeParams {
   float* part_o;    // [kMaxCtas*2][rows][D]
   float* part_ml;   // [kMaxCtas*2][rows][2]
   int32_t* header;  // [items + 3]: prefix[items+1], per, total
+  int32_t* owner;   // [kMaxCtas]: item that CTA c must have merged at boundary c|c+1, or -1
   int64_t q_stride, out_stride;
   int batch, H, Hkv, G, block_size, bt_stride;
   int hg_count;  // head groups per sequence = Hkv / HKV_CTA
@@ -227,6 +228,7 @@ paged_decode_kernel(const __grid_constant__ CUtensorMap tmK,
   int stage = 0, phase = 0;
   int seg_index = 0;
   int t = lo;
+  int own_item = -1;   // split item whose first piece is this CTA's last segment
   int it = total > 0 && lo < hi ? find_item(prefix, items, lo) : items;
   while (t < hi) {
     const int item_t0 = prefix[it], ntiles = prefix[it + 1] - item_t0;
@@ -388,15 +390,18 @@ paged_decode_kernel(const __grid_constant__ CUtensorMap tmK,
         }
       }
     }
+    if (j1 < ntiles && item_t0 / per == (int)blockIdx.x) own_item = it;
     t += j1 - j0;
     ++seg_index;
     do { ++it; } while (it < items && prefix[it + 1] == prefix[it]);
   }
+  if (threadIdx.x == 0) p.owner[blockIdx.x] = own_item;   // read by the combine kernel
 }
 
 // Combine kernel: merges the partial results of items whose tiles were split across CTAs.
 // One CTA per range boundary c | c+1: the item that straddles that boundary is merged by the
-// FIRST boundary it straddles (every other block exits at once), so the grid is #CTAs-1 blocks
+// FIRST boundary it straddles -- the decode CTA on the left of that boundary records the item in
+// owner[c] -- (every other block exits after one load), so the grid is #CTAs-1 blocks
 // instead of one block per (item, row). gridDim.y == 1 (large batches, few pieces per item):
 // the 8 warps take the rows round-robin and fold the pieces serially. gridDim.y == rows (small
 // batches, one item cut into up to #CTAs pieces): block (c, r) folds row r, its 8 warps split
@@ -411,17 +416,11 @@ decode_combine_kernel(const DecodeParams p, int rows /* = HKV_CTA*G */) {
   const int items = p.batch * p.hg_count;
   const int per = p.header[items + 1], total = p.header[items + 2];
   const int c = blockIdx.x;
-  const int tb = (c + 1) * per;                 // first tile of range c+1
-  if (tb >= total) return;
-  int lo = 0, hi = items;                       // item holding tile tb
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (p.header[mid] <= tb) lo = mid; else hi = mid;
-  }
-  const int it = lo, t0 = p.header[it], t1 = p.header[it + 1];
-  if (t0 == tb) return;                         // item starts exactly here: not cut at this boundary
-  const int c_first = t0 / per, c_last = (t1 - 1) / per;
-  if (c_first != c) return;                     // an earlier boundary owns this item
+  const int it = p.owner[c];                    // item cut at this boundary and first cut here
+  if (it < 0) return;
+  (void)total;
+  const int t0 = p.header[it], t1 = p.header[it + 1];
+  const int c_first = c, c_last = (t1 - 1) / per;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = it / p.hg_count, hg = it - b * p.hg_count;
   T* obase = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_stride + (int64_t)hg * rows * D;
@@ -610,7 +609,8 @@ extern "C" size_t b200_paged_decode_attn_workspace_size(int32_t batch, int32_t n
   const int G = num_heads / num_kv_heads;
   const size_t rows = (size_t)hkv_cta * G;
   const size_t items = (size_t)batch * (num_kv_heads / hkv_cta);
-  return align_up((items + 3) * 4, 256) + align_up((size_t)kMaxCtas * 2 * rows * head_dim * 4, 256) +
+  return align_up((items + 3) * 4, 256) + align_up((size_t)kMaxCtas * 4, 256) +
+         align_up((size_t)kMaxCtas * 2 * rows * head_dim * 4, 256) +
          align_up((size_t)kMaxCtas * 2 * rows * 2 * 4, 256);
 }
 
@@ -664,6 +664,8 @@ extern "C" int b200_paged_decode_attn(void* out, const void* q, const void* k_ca
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   p.header = reinterpret_cast<int32_t*>(ws);
   ws += align_up((items + 3) * 4, 256);
+  p.owner = reinterpret_cast<int32_t*>(ws);
+  ws += align_up((size_t)kMaxCtas * 4, 256);
   p.part_o = reinterpret_cast<float*>(ws);
   ws += align_up((size_t)kMaxCtas * 2 * rows * head_dim * 4, 256);
   p.part_ml = reinterpret_cast<float*>(ws);
