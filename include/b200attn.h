@@ -212,6 +212,20 @@ int b200_allreduce_add_rmsnorm(void* out, void* residual, const void* weight, fl
                                void* const* peer_flags, void* state, int32_t world, int32_t rank,
                                int32_t dtype, b200_stream_t stream);
 
+/* C1 (fused), two-shot form for messages whose one-shot traffic ((world-1) full copies pulled by
+ * every rank) is bandwidth-bound. Same contract and result bits as b200_allreduce_add_rmsnorm; in
+ * addition peer_gather[r] is rank r's gather buffer [rows, hidden] (dtype) as addressable from this
+ * rank, peer_flags[r] must hold >= 16 uint32 (the first 8 are shared with the one-shot form, so both
+ * forms may be mixed call by call as long as every rank makes the same choice), `state` is the same
+ * local uint32[4]. Rank r reduces rows [r*ceil(rows/world), ...) and pushes the sums to every rank;
+ * NVLink bytes per rank: 2*(world-1)/world * rows*hidden*sizeof(dtype). The grid is capped at one
+ * CTA per SM (every CTA spins on peer flags and must be co-resident). */
+int b200_allreduce_add_rmsnorm_twoshot(void* out, void* residual, const void* weight, float eps,
+                                       int32_t rows, int32_t hidden, const void* const* peer_bufs,
+                                       void* const* peer_gather, void* const* peer_flags,
+                                       void* state, int32_t world, int32_t rank, int32_t dtype,
+                                       b200_stream_t stream);
+
 /* Set-up helpers for the peer buffers (NOT hot path: they allocate / map memory, synchronously).
  * alloc: cudaMalloc + zero; get/open_handle: CUDA IPC (64-byte handle, peer access enabled
  * lazily); all return 0 or a cudaError_t value. */

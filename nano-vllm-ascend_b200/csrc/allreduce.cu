@@ -14,6 +14,13 @@
 // alternate between consecutive calls, which makes a trailing barrier unnecessary (a rank can only
 // pass the start barrier of call e+1 after every rank has finished reading call e).
 // Bytes over NVLink per rank: (world-1) * T * hidden * 2; latency-bound at decode sizes.
+//
+// Two-shot variant (allreduce_add_rmsnorm_twoshot_kernel) for messages where pulling world-1 full
+// copies is bandwidth-bound (Qwen3-32B TP=8: 18 MB in per call): rank r reduces only its slice of
+// the rows (reads (world-1)/world of one message) and PUSHES the bf16 sums into every rank's gather
+// buffer (writes the same amount); after a second flag barrier every rank runs the residual-add +
+// RMSNorm over all rows from its local gather buffer. NVLink bytes per rank: 2*(world-1)/world *
+// T*hidden*2 instead of (world-1) * T*hidden*2 -- 4.6 MB instead of 18 MB in that configuration.
 #include "common.cuh"
 
 #include <cstring>
@@ -38,28 +45,34 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
+// fp32 sum, in rank order, of the 8 elements each rank contributed (bitwise identical wherever it
+// is evaluated)
 template <typename T>
-__global__ void __launch_bounds__(256)
-allreduce_add_rmsnorm_kernel(const ArParams p, T* __restrict__ out, T* __restrict__ residual,
-                             const T* __restrict__ weight, float eps, int hidden) {
-  __shared__ float red[32];
-  pdl_wait();
-  __shared__ uint32_t s_ticket;
-  const uint32_t epoch = p.state[0] + 1;           // read before anyone can advance it (see end)
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[2], 1u);
-  __syncthreads();
-  if (s_ticket == 0 && threadIdx.x < p.world) {    // whichever block starts first publishes
-    __threadfence_system();                        // the GEMM's partial is visible system-wide
-    st_release_sys(p.flags[threadIdx.x] + p.rank, epoch);
-  }
-  if (threadIdx.x < p.world) {
-    const uint32_t* mine = p.flags[p.rank] + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+__device__ __forceinline__ void sum_parts(const uint4 (&part)[kMaxWorld], int world, float (&acc)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMaxWorld; ++r) {
+    if (r < world) {
+      const uint32_t w[4] = {part[r].x, part[r].y, part[r].z, part[r].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack2<T>(w[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
     }
   }
-  __syncthreads();
+}
 
-  const int64_t row = blockIdx.x;
+// One row of  residual <- cast(y) + residual ; out <- RMSNorm(that sum) * weight  with the rounding
+// points of the reference (layers/layernorm.py:27-38): y materialised in T, add in fp32, norm in fp32.
+// load_sum(idx, acc) yields the 8 summed elements of 16-byte vector idx = row * hidden/8 + v.
+// blockDim.x * 4 vectors cover a row (hidden <= 8192). `red`: 32 floats of shared memory.
+template <typename T, typename LoadSum>
+__device__ __forceinline__ void add_rmsnorm_row(int64_t row, int hidden, T* __restrict__ out,
+                                                T* __restrict__ residual, const T* __restrict__ weight,
+                                                float eps, float* red, LoadSum load_sum) {
   const int nvec = hidden / 8;
   uint4* rrow = reinterpret_cast<uint4*>(residual + row * hidden);
   constexpr int kVec = 4;
@@ -70,24 +83,7 @@ allreduce_add_rmsnorm_kernel(const ArParams p, T* __restrict__ out, T* __restric
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
       float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      uint4 part[kMaxWorld];
-#pragma unroll
-      for (int r = 0; r < kMaxWorld; ++r)
-        if (r < p.world) part[r] = __ldcg(reinterpret_cast<const uint4*>(p.bufs[r]) + row * nvec + v);
-#pragma unroll
-      for (int r = 0; r < kMaxWorld; ++r) {
-        if (r < p.world) {
-          const uint32_t w[4] = {part[r].x, part[r].y, part[r].z, part[r].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack2<T>(w[j]);
-            acc[2 * j] += f.x;
-            acc[2 * j + 1] += f.y;
-          }
-        }
-      }
+      load_sum(row * nvec + v, acc);
       const uint4 rv = rrow[v];
       const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
       uint32_t ow[4];
@@ -138,6 +134,36 @@ allreduce_add_rmsnorm_kernel(const ArParams p, T* __restrict__ out, T* __restric
       orow[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+allreduce_add_rmsnorm_kernel(const ArParams p, T* __restrict__ out, T* __restrict__ residual,
+                             const T* __restrict__ weight, float eps, int hidden) {
+  __shared__ float red[32];
+  pdl_wait();
+  __shared__ uint32_t s_ticket;
+  const uint32_t epoch = p.state[0] + 1;           // read before anyone can advance it (see end)
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[2], 1u);
+  __syncthreads();
+  if (s_ticket == 0 && threadIdx.x < p.world) {    // whichever block starts first publishes
+    __threadfence_system();                        // the GEMM's partial is visible system-wide
+    st_release_sys(p.flags[threadIdx.x] + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+
+  add_rmsnorm_row<T>(blockIdx.x, hidden, out, residual, weight, eps, red, [&](int64_t idx, float (&acc)[8]) {
+    uint4 part[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < p.world) part[r] = __ldcg(reinterpret_cast<const uint4*>(p.bufs[r]) + idx);
+    sum_parts<T>(part, p.world, acc);
+  });
   // the block that finishes last advances the epoch (every block has read it by then)
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -145,6 +171,102 @@ allreduce_add_rmsnorm_kernel(const ArParams p, T* __restrict__ out, T* __restric
     if (done == gridDim.x - 1) {
       p.state[1] = 0;
       p.state[2] = 0;
+      __threadfence();
+      p.state[0] = epoch;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-shot variant. state: [0] epoch, [1] finished-block counter, [2] start ticket, [3] blocks done
+// with the reduce-scatter phase. flags: uint32[2*kMaxWorld] per rank -- [0..8) start barrier (shared
+// with the one-shot kernel, same epoch sequence), [8..16) "slice pushed" barrier.
+// Every CTA spins on flags, so the whole grid must be co-resident: the host caps it at one CTA per SM.
+struct Ar2Params {
+  ArParams base;
+  void* gather[kMaxWorld];       // rank r's gather buffer [rows, hidden] as seen from this rank
+  int rows;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+allreduce_add_rmsnorm_twoshot_kernel(const Ar2Params q, T* __restrict__ out, T* __restrict__ residual,
+                                     const T* __restrict__ weight, float eps, int hidden) {
+  __shared__ float red[32];
+  __shared__ uint32_t s_ticket;
+  const ArParams& p = q.base;
+  pdl_wait();
+  const uint32_t epoch = p.state[0] + 1;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[2], 1u);
+  __syncthreads();
+  if (s_ticket == 0 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: reduce my slice of the rows, push the sums (in T) to every rank's gather buffer
+  const int nvec = hidden / 8;
+  const int slice = (q.rows + p.world - 1) / p.world;
+  const int row0 = min(p.rank * slice, q.rows), row1 = min(row0 + slice, q.rows);
+  const int64_t v_begin = (int64_t)row0 * nvec, v_end = (int64_t)row1 * nvec;
+  for (int64_t idx = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < v_end;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    uint4 part[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < p.world) part[r] = __ldcg(reinterpret_cast<const uint4*>(p.bufs[r]) + idx);
+    float acc[8];
+    sum_parts<T>(part, p.world, acc);
+    const uint4 y = make_uint4(pack2<T>(acc[0], acc[1]), pack2<T>(acc[2], acc[3]),
+                               pack2<T>(acc[4], acc[5]), pack2<T>(acc[6], acc[7]));
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < p.world) reinterpret_cast<uint4*>(q.gather[r])[idx] = y;
+  }
+  // ---- barrier 2: the last CTA of this rank to finish its pushes tells every peer
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[3], 1u);
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + kMaxWorld + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + kMaxWorld + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: residual add + RMSNorm over all rows from the local gather buffer
+  const uint4* gathered = reinterpret_cast<const uint4*>(q.gather[p.rank]);
+  for (int row = blockIdx.x; row < q.rows; row += gridDim.x) {
+    add_rmsnorm_row<T>(row, hidden, out, residual, weight, eps, red, [&](int64_t idx, float (&acc)[8]) {
+      const uint4 y = __ldcg(gathered + idx);
+      const uint32_t w[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack2<T>(w[j]);
+        acc[2 * j] = f.x;
+        acc[2 * j + 1] = f.y;
+      }
+    });
+    __syncthreads();                 // `red` is reused by the next row
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(&p.state[1], 1u);
+    if (done == gridDim.x - 1) {
+      p.state[1] = 0;
+      p.state[2] = 0;
+      p.state[3] = 0;
       __threadfence();
       p.state[0] = epoch;
     }
@@ -191,6 +313,49 @@ extern "C" int b200_allreduce_add_rmsnorm(void* out, void* residual, const void*
   else
     launch_pdl(allreduce_add_rmsnorm_kernel<__half>, dim3(rows), dim3(threads), 0, (cudaStream_t)stream,
                p, (__half*)out, (__half*)residual, (const __half*)weight, eps, hidden);
+  return finish_launch();
+}
+
+extern "C" int b200_allreduce_add_rmsnorm_twoshot(void* out, void* residual, const void* weight,
+                                                  float eps, int32_t rows, int32_t hidden,
+                                                  const void* const* peer_bufs,
+                                                  void* const* peer_gather, void* const* peer_flags,
+                                                  void* state, int32_t world, int32_t rank,
+                                                  int32_t dtype, b200_stream_t stream) {
+  B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
+  B200_RETURN_IF(rows < 0 || hidden <= 0 || world < 2 || world > kMaxWorld || rank < 0 || rank >= world,
+                 B200_ERR_BAD_SHAPE);
+  if (rows == 0) return B200_OK;
+  B200_RETURN_IF(!out || !residual || !weight || !peer_bufs || !peer_gather || !peer_flags || !state,
+                 B200_ERR_NULL_POINTER);
+  B200_RETURN_IF(hidden % 8 != 0 || !aligned16(out) || !aligned16(residual) || !aligned16(weight),
+                 B200_ERR_MISALIGNED);
+  B200_RETURN_IF(hidden > 8 * 256 * 4, B200_ERR_UNSUPPORTED);
+  Ar2Params q;
+  for (int r = 0; r < world; ++r) {
+    B200_RETURN_IF(!peer_bufs[r] || !peer_gather[r] || !peer_flags[r], B200_ERR_NULL_POINTER);
+    B200_RETURN_IF(!aligned16(peer_bufs[r]) || !aligned16(peer_gather[r]), B200_ERR_MISALIGNED);
+    q.base.bufs[r] = peer_bufs[r];
+    q.base.flags[r] = reinterpret_cast<uint32_t*>(peer_flags[r]);
+    q.gather[r] = peer_gather[r];
+  }
+  q.base.state = reinterpret_cast<uint32_t*>(state);
+  q.base.world = world;
+  q.base.rank = rank;
+  q.rows = rows;
+  // every CTA spins on peer flags: keep the grid co-resident (<= one CTA per SM) and balanced
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int rows_per_cta = (rows + sms - 1) / sms;
+  const int grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  if (dtype == B200_DTYPE_BF16)
+    launch_pdl(allreduce_add_rmsnorm_twoshot_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0,
+               (cudaStream_t)stream, q, (__nv_bfloat16*)out, (__nv_bfloat16*)residual,
+               (const __nv_bfloat16*)weight, eps, hidden);
+  else
+    launch_pdl(allreduce_add_rmsnorm_twoshot_kernel<__half>, dim3(grid), dim3(256), 0,
+               (cudaStream_t)stream, q, (__half*)out, (__half*)residual, (const __half*)weight, eps,
+               hidden);
   return finish_launch();
 }
 

@@ -1,14 +1,17 @@
 """Peer-memory communicator for the fused tensor-parallel all-reduce (C1).
 
 One cudaMalloc'd region per rank, mapped into every other rank with CUDA IPC (NVLink P2P):
-  [ partial buffer 0 | partial buffer 1 | flags (uint32[8]) | state (uint32[4]) ]
+  [ partial buffer 0 | partial buffer 1 | gather buffer | flags (uint32[16]) | state (uint32[4]) ]
 The row-parallel GEMMs write their partial products straight into partial buffer `parity`; the
-fused kernel (b200_allreduce_add_rmsnorm) reads every rank's copy. Set-up uses
+fused kernel reads every rank's copy: one-shot (b200_allreduce_add_rmsnorm, every rank pulls all
+copies) for small messages, two-shot (b200_allreduce_add_rmsnorm_twoshot, each rank reduces a slice
+of the rows and pushes the sums into every rank's gather buffer) for larger ones. Set-up uses
 torch.distributed only to exchange the 64-byte IPC handles.
 """
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -33,7 +36,7 @@ class PeerAllReduce:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device
         self.max_bytes = int(max_bytes)
-        total = 2 * self.max_bytes + 2 * self.FLAG_BYTES
+        total = 3 * self.max_bytes + 2 * self.FLAG_BYTES
         ptr = ctypes.c_void_p()
         _C.check(lib.b200_comm_alloc(total, ctypes.byref(ptr)), "b200_comm_alloc")
         self.local_ptr = ptr.value
@@ -52,8 +55,12 @@ class PeerAllReduce:
         self.local = torch.as_tensor(_RawCudaBuffer(self.local_ptr, total), device=device)
         arr = ctypes.c_void_p * self.world
         self._bufs = [arr(*[p + par * self.max_bytes for p in self.peer_ptrs]) for par in (0, 1)]
-        self._flags = arr(*[p + 2 * self.max_bytes for p in self.peer_ptrs])
-        self._state = self.local_ptr + 2 * self.max_bytes + self.FLAG_BYTES
+        self._gather = arr(*[p + 2 * self.max_bytes for p in self.peer_ptrs])
+        self._flags = arr(*[p + 3 * self.max_bytes for p in self.peer_ptrs])
+        self._state = self.local_ptr + 3 * self.max_bytes + self.FLAG_BYTES
+        # two-shot kernel: compiled and unit-tested on 2 GPUs only when enabled; opt-in until the
+        # multi-GPU validation recorded in DESIGN.md section 6 is done
+        self.two_shot = os.environ.get("B200_TWOSHOT_ALLREDUCE", "0") == "1"
         self._parity = 0
         self.pending = None          # (tensor, parity) written by the last deferred row-parallel GEMM
         dist.barrier()
@@ -64,10 +71,17 @@ class PeerAllReduce:
     # (18 MB in per call) is bandwidth-bound at ~26 us per call.
     ONE_SHOT_MAX_INCOMING = 4 << 20
 
-    def fits(self, rows: int, hidden: int, itemsize: int) -> bool:
+    def mode(self, rows: int, hidden: int, itemsize: int) -> str | None:
+        """"one" / "two" (shot) when the fused kernel takes this message, None for NCCL."""
         nbytes = rows * hidden * itemsize
-        return (nbytes <= self.max_bytes and (self.world - 1) * nbytes <= self.ONE_SHOT_MAX_INCOMING
-                and hidden % 8 == 0 and hidden <= 8192)
+        if nbytes > self.max_bytes or hidden % 8 != 0 or hidden > 8192:
+            return None
+        if (self.world - 1) * nbytes <= self.ONE_SHOT_MAX_INCOMING:
+            return "one"
+        return "two" if self.two_shot and rows >= self.world else None
+
+    def fits(self, rows: int, hidden: int, itemsize: int) -> bool:
+        return self.mode(rows, hidden, itemsize) is not None
 
     def partial_buffer(self, rows: int, hidden: int, dtype: torch.dtype) -> torch.Tensor:
         """View of this rank's next partial buffer; the GEMM writes its output here."""
@@ -78,18 +92,25 @@ class PeerAllReduce:
         self.pending = (view, parity)
         return view
 
-    def allreduce_add_rmsnorm(self, out, residual, weight, eps):
+    def allreduce_add_rmsnorm(self, out, residual, weight, eps, mode: str | None = None):
         """out <- RMSNorm(sum_r partial_r + residual) * weight; residual updated in place.
         `out` may be any [rows, hidden] tensor (normally a fresh one; the partial buffer itself must
-        not be used: peers may still be reading it)."""
+        not be used: peers may still be reading it). `mode` forces "one"/"two" (tests); every rank
+        must pass the same value."""
         view, parity = self.pending
         self.pending = None
         rows, hidden = view.shape
         from .ops import _dt, _stream
-        _C.check(self.lib.b200_allreduce_add_rmsnorm(
-            out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
-            self._bufs[parity], self._flags, self._state, self.world, self.rank, _dt(view), _stream()),
-            "b200_allreduce_add_rmsnorm")
+        if (mode or self.mode(rows, hidden, view.dtype.itemsize)) == "two":
+            _C.check(self.lib.b200_allreduce_add_rmsnorm_twoshot(
+                out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
+                self._bufs[parity], self._gather, self._flags, self._state, self.world, self.rank,
+                _dt(view), _stream()), "b200_allreduce_add_rmsnorm_twoshot")
+        else:
+            _C.check(self.lib.b200_allreduce_add_rmsnorm(
+                out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
+                self._bufs[parity], self._flags, self._state, self.world, self.rank, _dt(view),
+                _stream()), "b200_allreduce_add_rmsnorm")
         return out, residual
 
     def close(self):

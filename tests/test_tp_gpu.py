@@ -36,7 +36,15 @@ def test_tp2_matches_tp1(enforce_eager):
     assert got == want
 
 
-def _ar_worker(rank, world, port, out_q):
+_ONE_SHOT_CASES = [(256, 1024, None), (1, 1024, None), (37, 5120, None), (256, 128, None), (5, 1024, None),
+                   (8, 2048, None)]
+# two-shot (row-sliced reduce + push) incl. rows < world, a ragged last slice, and one-/two-shot
+# calls interleaved on the same flags/epoch sequence
+_TWO_SHOT_CASES = [(256, 5120, "two"), (37, 5120, "two"), (1, 1024, "two"), (8, 2048, "one"),
+                   (3, 2048, "two"), (256, 1024, "two"), (5, 8192, "one"), (255, 4096, "two")]
+
+
+def _ar_worker(rank, world, port, out_q, cases):
     import os
     import sys
     import torch
@@ -50,7 +58,7 @@ def _ar_worker(rank, world, port, out_q):
     from oracle import layers_ref as L
     comm = PeerAllReduce(torch.device("cuda", rank))
     ok = True
-    for it, (rows, hidden) in enumerate([(256, 1024), (1, 1024), (37, 5120), (256, 128), (5, 1024), (8, 2048)]):
+    for it, (rows, hidden, mode) in enumerate(cases):
         g = torch.Generator().manual_seed(100 + it)                  # same stream on every rank
         parts = [torch.randn(rows, hidden, generator=g).bfloat16() for _ in range(world)]
         res = torch.randn(rows, hidden, generator=g).bfloat16()
@@ -62,7 +70,7 @@ def _ar_worker(rank, world, port, out_q):
         buf.copy_(parts[rank].cuda())
         res_d = res.cuda()
         out = torch.empty(rows, hidden, dtype=torch.bfloat16, device="cuda")
-        comm.allreduce_add_rmsnorm(out, res_d, w.cuda(), 1e-6)
+        comm.allreduce_add_rmsnorm(out, res_d, w.cuda(), 1e-6, mode=mode)
         torch.cuda.synchronize()
         d_out = (out.cpu().float() - want.float()).abs().max().item()
         d_res = (res_d.cpu().float() - want_res.float()).abs().max().item()
@@ -74,17 +82,33 @@ def _ar_worker(rank, world, port, out_q):
     dist.destroy_process_group()
 
 
+def _run_ar_workers(world, port, cases):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ar_worker, args=(r, world, port, q, cases), daemon=True)
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        results = dict(q.get(timeout=180) for _ in range(world))
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:                  # a rank stuck in a flag spin loop must not outlive the test
+            if p.is_alive():
+                p.kill()
+    return results
+
+
 def test_fused_peer_allreduce_add_rmsnorm_kernel():
     """b200_allreduce_add_rmsnorm on 2 GPUs (CUDA IPC peer buffers over NVLink) against
     all-reduce (sum materialised in bf16) followed by the reference's add_rms_forward."""
     _need_gpus(2)
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_ar_worker, args=(r, 2, 28031, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = dict(q.get(timeout=180) for _ in range(2))
-    for p in procs:
-        p.join(timeout=60)
-    assert results == {0: True, 1: True}
+    assert _run_ar_workers(2, 28031, _ONE_SHOT_CASES) == {0: True, 1: True}
+
+
+def test_fused_peer_allreduce_twoshot_kernel():
+    """b200_allreduce_add_rmsnorm_twoshot (reduce a row slice, push the sums, norm locally)."""
+    _need_gpus(2)
+    assert _run_ar_workers(2, 28033, _TWO_SHOT_CASES) == {0: True, 1: True}
