@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mem-util", type=float, default=0.7, help="gpu_memory_utilization of the engine")
     ap.add_argument("--cpu-sample-seqs", type=int, default=32)
+    ap.add_argument("--kv-cache-dtype", default="auto", choices=["auto", "fp8"],
+                    help="fp8: e4m3 KV cache (an extra line; the contract line is the default bf16 cache)")
     return ap.parse_args()
 
 
@@ -172,7 +174,8 @@ def workload_config(args, world):
                         f"kvcache_block_size {args.block_size}, CUDA-graph decode (BASELINE configs[1])",
             "global_batch": args.batch * (1 if args.tp else world), "seq_len": args.ctx,
             "parallelism": f"{par}x{world}" if world > 1 else "single",
-            "l2": "inputs exceed L2 (>= 28 GiB of KV streamed per step)"}
+            "l2": "inputs exceed L2 (>= 28 GiB of KV streamed per step)",
+            **({} if args.kv_cache_dtype == "auto" else {"kv_cache_dtype": "fp8_e4m3"})}
 
 
 # ------------------------------------------------------------------ the GPU arm
@@ -205,7 +208,7 @@ def main():
     llm = LLM(args.model, kvcache_block_size=args.block_size, max_num_seqs=B,
               max_model_len=max(4096, max_len), max_num_batched_tokens=16384,
               tensor_parallel_size=world if args.tp else 1, distributed_launch="env",
-              gpu_memory_utilization=args.mem_util, seed=0)
+              gpu_memory_utilization=args.mem_util, kv_cache_dtype=args.kv_cache_dtype, seed=0)
     runner = llm.model_runner
     spec = runner.spec
     rnd = random.Random(rank if not args.tp else 0)
@@ -283,10 +286,12 @@ def main():
     ws = ops.decode_workspace(B, Hq, Hkv, D, q.device)
     L = spec.num_layers
 
+    attn_fn = ops.paged_decode_attn if args.kv_cache_dtype == "auto" else ops.paged_decode_attn_fp8
+
     def attn_pass():
         for layer in range(L):
-            ops.paged_decode_attn(q, runner.kv_cache[0, layer], runner.kv_cache[1, layer],
-                                  runner.d_tables[:B], runner.d_ctx[:B], D ** -0.5, Hkv, out=o, workspace=ws)
+            attn_fn(q, runner.kv_cache[0, layer], runner.kv_cache[1, layer],
+                    runner.d_tables[:B], runner.d_ctx[:B], D ** -0.5, Hkv, out=o, workspace=ws)
     for _ in range(3):
         attn_pass()
     barrier()
@@ -300,12 +305,12 @@ def main():
     dbg(rank, 'attn loop done')
     clk = clocks.stop()
     ctx_sum = int(runner.d_ctx[:B].sum().item())
-    attn_bytes = ctx_sum * 2 * Hkv * D * runner.dtype.itemsize          # algorithmic bytes / launch
+    attn_bytes = ctx_sum * 2 * Hkv * D * runner.kv_cache.dtype.itemsize  # algorithmic bytes / launch
     peak, peak_src = peaks()
     achieved = attn_bytes / attn_launch_s / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "decode_attn_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.kv_cache_dtype == "auto":
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
 
@@ -323,7 +328,8 @@ def main():
         "ttft_p50_ms": ttft_p50, "ttft_max_ms": ttfts[-1], "prefill_steps": prefill_steps,
         "prefill_tokens_per_s": world * B * ctx / prefill_s if not args.tp else B * ctx / prefill_s,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "paged_decode_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "paged_decode_kernel" if args.kv_cache_dtype == "auto"
+                     else "paged_decode_fp8_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": attn_bytes,
                      "us_per_launch": attn_launch_s * 1e6,

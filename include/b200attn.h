@@ -114,6 +114,32 @@ int b200_paged_decode_attn(void* out, const void* q, const void* k_cache, const 
                            b200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
+ * K1/K2 + K6 over an FP8 (e4m3) KV cache -- SURVEY.md 8f row f3. An EXTENSION of the path: the
+ * reference keeps its caches in the model dtype (engine/model_runner.py:218-229); nothing in it is
+ * replaced by these two entry points, they halve the bytes K6 streams.
+ * Cache element = e4m3(x * (1/scale)), round-to-nearest-even, saturating at +-448; k_scale and
+ * v_scale are per-tensor fp32 scales (> 0). Caches: [num_blocks, block_size, num_kv_heads*head_dim]
+ * BYTES, contiguous. Everything else (layouts, slots, block tables, context_len == 0 rows,
+ * workspace, return codes) is as for b200_reshape_and_cache[_2d] / b200_paged_decode_attn;
+ * `dtype` is the element type of key/value/q/out. Attention is evaluated over the de-quantised
+ * values k8*k_scale, v8*v_scale with fp32 softmax and accumulation.
+ * Extra limits: q/out 8-byte aligned with strides % 4 == 0; head_dim 64 needs >= 2 kv heads.
+ * ------------------------------------------------------------------------------- */
+int b200_reshape_and_cache_fp8(const void* key, const void* value, void* k_cache, void* v_cache,
+                               const int32_t* slots, int32_t slot_is_2d, int32_t num_tokens,
+                               int32_t num_kv_heads, int32_t head_dim, int64_t key_stride,
+                               int64_t value_stride, int32_t num_blocks, int32_t block_size,
+                               float k_scale, float v_scale, int32_t dtype, b200_stream_t stream);
+int b200_paged_decode_attn_fp8(void* out, const void* q, const void* k_cache, const void* v_cache,
+                               const int32_t* block_tables, const int32_t* context_lens,
+                               int32_t batch, int32_t num_heads, int32_t num_kv_heads,
+                               int32_t head_dim, int64_t q_stride, int64_t out_stride,
+                               int32_t num_blocks, int32_t block_size, int32_t block_table_stride,
+                               float scale, float k_scale, float v_scale, void* workspace,
+                               size_t workspace_bytes, int32_t num_ctas, int32_t dtype,
+                               b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
  * K4/K5  varlen causal prefill flash-attention.
  * Replaces: npu_fused_infer_attention_score_v2 TND, sparse_mode=3  layers/attention.py:49-59
  *           flash_attn_varlen_func(causal=True[, block_table])     layers/attention_ori.py:63-70

@@ -26,7 +26,10 @@ inline int finish_launch(int kernels = 1) {
   return B200_OK;
 }
 
-// TMA tensor map (cached by key) over a row-major 16-bit matrix; see decode_attn.cu
+// TMA tensor map (cached by key) over a row-major matrix viewed as 128-byte-wide panels; `dtype`
+// is B200_DTYPE_BF16 / B200_DTYPE_F16 (64 elements per panel row) or kPanelU8 (128 one-byte
+// elements: the fp8 KV cache); see decode_attn.cu
+constexpr int kPanelU8 = 2;
 int get_panel_map(const void* base, int64_t rows, int64_t row_bytes, int chunks, int rows_box,
                   int chunks_box, int dtype, CUtensorMap* out);
 

@@ -82,11 +82,17 @@ class Config:
     distributed_launch: str = "spawn"  # "spawn": reference style (rank 0 spawns workers);
                                        # "env": every rank is already running (torchrun/SPMD)
     prefix_hit_prefill: bool = False   # feed only uncached prompt tokens (attention_ori semantics)
+    kv_cache_dtype: str = "auto"       # "auto": the model dtype (reference behaviour); "fp8" /
+                                       # "fp8_e4m3": e4m3 bytes, per-tensor scale 1.0
     device = "cuda"
 
     def __post_init__(self):
         assert self.kvcache_block_size % 16 == 0
         assert 1 <= self.tensor_parallel_size <= 8
+        assert self.kv_cache_dtype in ("auto", "fp8", "fp8_e4m3"), self.kv_cache_dtype
+        if self.kv_cache_dtype != "auto" and self.prefix_hit_prefill:
+            raise ValueError("prefix_hit_prefill reads K/V back from the cache with the prefill kernel, "
+                             "which takes 16-bit caches only; use kv_cache_dtype='auto' with it")
         if self.hf_config is None:
             if os.path.isdir(self.model):
                 from transformers import AutoConfig

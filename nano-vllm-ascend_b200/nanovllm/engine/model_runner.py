@@ -184,7 +184,9 @@ class ModelRunner:
     def _allocate_kv_cache(self):
         cfg, spec = self.config, self.spec
         kv_heads = spec.num_kv_heads // self.world_size
-        block_bytes = 2 * spec.num_layers * self.block_size * kv_heads * spec.head_dim * self.dtype.itemsize
+        # e4m3 caches are kept as raw bytes (uint8); the attention layers dispatch on that dtype
+        cache_dtype = self.dtype if cfg.kv_cache_dtype == "auto" else torch.uint8
+        block_bytes = 2 * spec.num_layers * self.block_size * kv_heads * spec.head_dim * cache_dtype.itemsize
         if cfg.num_kvcache_blocks <= 0:
             free, total = torch.cuda.mem_get_info()
             stats = torch.cuda.memory_stats()
@@ -199,7 +201,7 @@ class ModelRunner:
             cfg.num_kvcache_blocks = int(n.item())
         assert cfg.num_kvcache_blocks > 1, "not enough memory for the KV cache"
         self.kv_cache = torch.zeros(2, spec.num_layers, cfg.num_kvcache_blocks, self.block_size,
-                                    kv_heads * spec.head_dim, dtype=self.dtype, device=self.device)
+                                    kv_heads * spec.head_dim, dtype=cache_dtype, device=self.device)
         layer = 0
         for module in self.model.modules():
             if hasattr(module, "k_cache") and hasattr(module, "v_cache"):

@@ -28,6 +28,13 @@ class Attention(nn.Module):
         self.layer_id = -1
         self.k_cache = torch.tensor([])
         self.v_cache = torch.tensor([])
+        # only read when the runner binds e4m3 (uint8) caches: cache = e4m3(x / scale)
+        self.k_scale = 1.0
+        self.v_scale = 1.0
+
+    @property
+    def fp8_cache(self) -> bool:
+        return self.k_cache.dtype in (torch.uint8, torch.float8_e4m3fn)
 
     def _as_heads(self, x, heads):
         return x.view(-1, heads, self.head_dim) if x.dim() == 2 else x
@@ -36,9 +43,12 @@ class Attention(nn.Module):
         """K1/K2: write this step's K/V rows at context.slot_mapping (flat or (block, offset))."""
         context = context or get_context()
         if self.k_cache.numel() and self.v_cache.numel():
-            ops.reshape_and_cache(self._as_heads(k, self.num_kv_heads),
-                                  self._as_heads(v, self.num_kv_heads), self.k_cache, self.v_cache,
-                                  context.slot_mapping)
+            k, v = self._as_heads(k, self.num_kv_heads), self._as_heads(v, self.num_kv_heads)
+            if self.fp8_cache:
+                ops.reshape_and_cache_fp8(k, v, self.k_cache, self.v_cache, context.slot_mapping,
+                                          self.k_scale, self.v_scale)
+            else:
+                ops.reshape_and_cache(k, v, self.k_cache, self.v_cache, context.slot_mapping)
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_stored: bool = False):
         """kv_stored=True: the caller already scattered K/V (fused K8 epilogue)."""
@@ -51,6 +61,8 @@ class Attention(nn.Module):
             self.store_kvcache(k, v, context)
         if context.is_prefill:
             if context.paged_prefill:
+                if self.fp8_cache:
+                    raise NotImplementedError("paged (prefix-hit) prefill over an fp8 KV cache")
                 return ops.prefill_varlen_attn(q, self.k_cache, self.v_cache, context.cu_seqlens_q,
                                                context.cu_seqlens_k, context.max_seqlen_q,
                                                context.max_seqlen_k, self.scale, self.num_kv_heads,
@@ -58,5 +70,9 @@ class Attention(nn.Module):
             return ops.prefill_varlen_attn(q, k, v, context.cu_seqlens_q, context.cu_seqlens_k,
                                            context.max_seqlen_q, context.max_seqlen_k, self.scale,
                                            self.num_kv_heads)
+        if self.fp8_cache:
+            return ops.paged_decode_attn_fp8(q, self.k_cache, self.v_cache, context.block_tables,
+                                             context.context_lens, self.scale, self.num_kv_heads,
+                                             self.k_scale, self.v_scale)
         return ops.paged_decode_attn(q, self.k_cache, self.v_cache, context.block_tables,
                                      context.context_lens, self.scale, self.num_kv_heads)

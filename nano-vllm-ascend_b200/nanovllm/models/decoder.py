@@ -84,17 +84,18 @@ class DecoderAttention(nn.Module):
         ctx = get_context()
         attn = self.attn
         have_cache = attn.k_cache.numel() > 0
+        fused_scatter = have_cache and not attn.fp8_cache     # K8 scatters 16-bit caches itself
         ops.qknorm_rope_cache(
             qkv, positions, self.rotary_emb.cos_sin_cache.view(-1, self.head_dim),
             None if self.q_norm is None else self.q_norm.weight,
             None if self.k_norm is None else self.k_norm.weight, self.eps,
-            attn.k_cache if have_cache else None, attn.v_cache if have_cache else None,
-            ctx.slot_mapping if have_cache else None, self.num_heads, self.num_kv_heads,
+            attn.k_cache if fused_scatter else None, attn.v_cache if fused_scatter else None,
+            ctx.slot_mapping if fused_scatter else None, self.num_heads, self.num_kv_heads,
             self.head_dim)
         q = qkv[:, :self.q_size].unflatten(1, (self.num_heads, self.head_dim))
         k = qkv[:, self.q_size:self.q_size + self.kv_size].unflatten(1, (self.num_kv_heads, self.head_dim))
         v = qkv[:, self.q_size + self.kv_size:].unflatten(1, (self.num_kv_heads, self.head_dim))
-        o = attn(q, k, v, kv_stored=True)
+        o = attn(q, k, v, kv_stored=not attn.fp8_cache)   # fp8 cache: attn runs the quantising scatter
         return self.o_proj(o)
 
 

@@ -76,6 +76,34 @@ def reshape_and_cache(key, value, k_cache, v_cache, slot_mapping):
              "b200_reshape_and_cache")
 
 
+def _is_fp8_cache(cache: torch.Tensor) -> bool:
+    return cache.dtype in (torch.uint8, torch.float8_e4m3fn)
+
+
+def reshape_and_cache_fp8(key, value, k_cache, v_cache, slot_mapping, k_scale=1.0, v_scale=1.0):
+    """K1/K2 into an e4m3 cache (uint8 / float8_e4m3fn tensors [nb, bs, Hkv*D]):
+    cache <- e4m3(x * (1/scale)), saturating. key/value [T, Hkv, D] bf16/fp16."""
+    _need_cuda(key, value, k_cache, v_cache, slot_mapping)
+    T, Hkv, D = key.shape
+    if value.shape != key.shape:
+        raise ValueError("key/value shape mismatch")
+    if key.stride(2) != 1 or key.stride(1) != D or value.stride(2) != 1 or value.stride(1) != D:
+        raise ValueError("key/value must be contiguous in (heads, head_dim)")
+    if slot_mapping.dtype != torch.int32 or not slot_mapping.is_contiguous():
+        raise TypeError("slot_mapping must be a contiguous int32 tensor")
+    if not (_is_fp8_cache(k_cache) and _is_fp8_cache(v_cache)):
+        raise TypeError("fp8 KV caches must be uint8 or float8_e4m3fn tensors")
+    nb, bs = _cache_dims(k_cache, Hkv * D)
+    two_d = slot_mapping.dim() == 2
+    if slot_mapping.shape[0] != T or (two_d and slot_mapping.shape[1] != 2):
+        raise ValueError(f"slot_mapping shape {tuple(slot_mapping.shape)} does not match {T} tokens")
+    _C.check(_C.load().b200_reshape_and_cache_fp8(
+        key.data_ptr(), value.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+        slot_mapping.data_ptr(), 1 if two_d else 0, T, Hkv, D,
+        key.stride(0) if T > 1 else Hkv * D, value.stride(0) if T > 1 else Hkv * D, nb, bs,
+        float(k_scale), float(v_scale), _dt(key), _stream()), "b200_reshape_and_cache_fp8")
+
+
 _decode_ws: dict = {}
 
 
@@ -114,6 +142,33 @@ def paged_decode_attn(q, k_cache, v_cache, block_tables, context_lens, scale, nu
         q.stride(0) if B > 1 else H * D, out.stride(0) if B > 1 else H * D, nb, bs,
         block_tables.stride(0), float(scale), workspace.data_ptr(), workspace.numel(),
         int(num_ctas), _dt(q), _stream()), "b200_paged_decode_attn")
+    return out
+
+
+def paged_decode_attn_fp8(q, k_cache, v_cache, block_tables, context_lens, scale, num_kv_heads,
+                          k_scale=1.0, v_scale=1.0, out=None, workspace=None, num_ctas=0):
+    """K6 over an e4m3 cache. q [B, H, D] bf16/fp16 -> out [B, H*D] in q's dtype."""
+    _need_cuda(q, k_cache, v_cache, block_tables, context_lens)
+    B, H, D = q.shape
+    if q.stride(2) != 1 or q.stride(1) != D:
+        raise ValueError("q must be contiguous in (heads, head_dim)")
+    if block_tables.dtype != torch.int32 or context_lens.dtype != torch.int32:
+        raise TypeError("block_tables/context_lens must be int32")
+    if block_tables.dim() != 2 or block_tables.stride(1) != 1 or not context_lens.is_contiguous():
+        raise ValueError("block_tables must be [B, max_blocks] row-major, context_lens contiguous")
+    if not (_is_fp8_cache(k_cache) and _is_fp8_cache(v_cache)):
+        raise TypeError("fp8 KV caches must be uint8 or float8_e4m3fn tensors")
+    nb, bs = _cache_dims(k_cache, num_kv_heads * D)
+    if out is None:
+        out = torch.empty(B, H * D, dtype=q.dtype, device=q.device)
+    if workspace is None:
+        workspace = decode_workspace(B, H, num_kv_heads, D, q.device)
+    _C.check(_C.load().b200_paged_decode_attn_fp8(
+        out.data_ptr(), q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+        block_tables.data_ptr(), context_lens.data_ptr(), B, H, num_kv_heads, D,
+        q.stride(0) if B > 1 else H * D, out.stride(0) if B > 1 else H * D, nb, bs,
+        block_tables.stride(0), float(scale), float(k_scale), float(v_scale), workspace.data_ptr(),
+        workspace.numel(), int(num_ctas), _dt(q), _stream()), "b200_paged_decode_attn_fp8")
     return out
 
 

@@ -141,3 +141,37 @@ def gather_paged_kv(k_cache, v_cache, block_tables, seq_lens):
         vv = v_cache[ids].reshape(-1, *v_cache.shape[2:])[:n]
         ks.append(kk), vs.append(vv), cu.append(cu[-1] + n)
     return torch.cat(ks), torch.cat(vs), torch.tensor(cu, dtype=torch.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# FP8 (e4m3) KV cache -- SURVEY.md 8f row f3. NOT a restatement of reference code: the reference
+# keeps its caches in the model dtype (engine/model_runner.py:218-229). This states the semantics
+# the fp8 kernels (csrc/decode_attn_fp8.cu) implement, with torch's own float8_e4m3fn cast as the
+# arithmetic authority, so the scatter can be checked bit for bit and attention against
+# ``decode_attention(mode="exact")`` over the de-quantised cache.
+E4M3_MAX = 448.0
+
+
+def quantize_e4m3(x, scale=1.0):
+    """bytes of e4m3(x * (1/scale)): the product and the reciprocal are fp32, the cast is round to
+    nearest even, saturating at +-448 (torch's cast would turn overflow into NaN, so clamp first)."""
+    inv = (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(scale, dtype=torch.float32))
+    y = (x.float() * inv).clamp(-E4M3_MAX, E4M3_MAX)
+    return y.to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def dequantize_e4m3(q, scale=1.0, dtype=torch.float32):
+    return (q.view(torch.float8_e4m3fn).float() * float(scale)).to(dtype)
+
+
+def store_kvcache_fp8(key, value, k_cache, v_cache, slot_mapping, block_size, k_scale=1.0, v_scale=1.0):
+    """store_kvcache into uint8 caches [nb, bs, G, D] holding e4m3 bytes (same slot rules)."""
+    store_kvcache(quantize_e4m3(key, k_scale), quantize_e4m3(value, v_scale), k_cache, v_cache,
+                  slot_mapping, block_size)
+
+
+def decode_attention_fp8(q, k_cache, v_cache, context_lens, block_tables, num_kv_heads, head_dim,
+                         scale, k_scale=1.0, v_scale=1.0):
+    """Exact-mode decode attention over the de-quantised e4m3 caches. Returns fp32 [B, H*D]."""
+    return decode_attention(q, dequantize_e4m3(k_cache, k_scale), dequantize_e4m3(v_cache, v_scale),
+                            context_lens, block_tables, num_kv_heads, head_dim, mode="exact", scale=scale)

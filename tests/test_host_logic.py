@@ -46,6 +46,17 @@ def test_bad_arguments_are_rejected_without_a_gpu():
                                       4, 0.1, one, 16, 0, 0, None) == -5               # workspace
     assert lib.b200_reshape_and_cache(one, one, one, one, one, 4, 8, 128, 1028, 1024, 8, 16, 0,
                                       None) == -4                                      # stride % 8
+    # fp8 KV-cache entry points: scales must be positive; head_dim 64 needs >= 2 kv heads; q 8-byte aligned
+    assert lib.b200_reshape_and_cache_fp8(one, one, one, one, one, 0, 4, 8, 128, 1024, 1024, 8, 16, 0.0,
+                                          1.0, 0, None) == -2
+    assert lib.b200_paged_decode_attn_fp8(one, one, one, one, one, one, 4, 8, 1, 64, 512, 512, 8, 16, 4,
+                                          0.1, 1.0, 1.0, one, 1 << 30, 0, 0, None) == -3
+    assert lib.b200_paged_decode_attn_fp8(one, ctypes.c_void_p(20), one, one, one, one, 4, 16, 8, 128,
+                                          2048, 2048, 8, 16, 4, 0.1, 1.0, 1.0, one, 1 << 30, 0, 0,
+                                          None) == -4
+    # two-shot all-reduce: world out of range
+    assert lib.b200_allreduce_add_rmsnorm_twoshot(one, one, one, 1e-6, 4, 64, one, one, one, one, 9, 0, 0,
+                                                  None) == -2
 
 
 def test_ops_refuse_cpu_tensors():
@@ -55,6 +66,33 @@ def test_ops_refuse_cpu_tensors():
         ops.rmsnorm(x, torch.ones(64, dtype=torch.bfloat16), 1e-6)
     with pytest.raises(RuntimeError, match="CUDA only"):
         ops.silu_and_mul(x)
+
+
+def test_fp8_oracle_and_fragment_map():
+    """The e4m3 statement the fp8 kernels are tested against: every finite byte round-trips, ties go
+    to even, overflow saturates at +-448; and the lane <-> data mapping of paged_decode_fp8_kernel
+    (permuted contraction index, even/odd column split), emulated lane by lane in numpy."""
+    from oracle import attention_ref as A
+    b = torch.arange(256, dtype=torch.uint8)
+    f = A.dequantize_e4m3(b)
+    finite = ~torch.isnan(f)
+    assert int(finite.sum()) == 254
+    assert torch.equal(A.quantize_e4m3(f[finite]), b[finite])
+    x = torch.tensor([1000.0, -1000.0, 1.0625, 1.1875, 464.0, 3 * 2.0 ** -11, 2.0 ** -10])  # last: tie -> even (0)
+    assert A.dequantize_e4m3(A.quantize_e4m3(x)).tolist() == [448.0, -448.0, 1.0, 1.25, 448.0, 2.0 ** -9, 0.0]
+    assert A.dequantize_e4m3(A.quantize_e4m3(x[:4], 2.0), 2.0).tolist() == [896.0, -896.0, 1.0, 1.25]
+    kc = torch.zeros(2, 16, 2, 8, dtype=torch.uint8)
+    vc = torch.zeros_like(kc)
+    k = torch.randn(3, 2, 8)
+    A.store_kvcache_fp8(k, k, kc, vc, torch.tensor([17, -1, 3]), 16, 0.5, 1.0)
+    assert torch.equal(kc[1, 1], A.quantize_e4m3(k[0], 0.5)) and torch.equal(vc[0, 3], A.quantize_e4m3(k[2]))
+    assert int(kc.count_nonzero()) <= 2 * 16
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import emulate_fp8_fragments as E
+    for D, heads in ((128, (0, 3)), (64, (0, 1))):
+        for h in heads:
+            E.run(D, h, G=2, valid=16, seed=1)
+            E.run(D, h, G=8, valid=5, seed=2)
 
 
 # ------------------------------------------------------------------ front-end contract
