@@ -266,21 +266,23 @@ paged_decode_fp8_kernel(const __grid_constant__ CUtensorMap tmK,
       if (active) {
         const uint32_t kb = smem_u32(kbuf + stage * TILE_BYTES) + unit_base;
         float s[2][4];
+        uint32_t kw[2][KSTEPS];     // token rows g (n = 0) and g + 8 (n = 1): word ks feeds MMA step ks
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
           s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
           const uint32_t rowaddr = kb + (n * 8 + g) * 128;
 #pragma unroll
           for (int i = 0; i < KSTEPS / 4; ++i) {
-            const uint4 kw = lds128(rowaddr + (((k_c16 + i) ^ g) << 4));
-            const uint32_t w[4] = {kw.x, kw.y, kw.z, kw.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int ks = 4 * i + e;
-              mma_16816<__half>(s[n], qa[ks][0], 0u, qa[ks][1], 0u, e4m3x2_to_f16x2(w[e] & 0xffffu),
-                                e4m3x2_to_f16x2(w[e] >> 16));
-            }
+            const uint4 x = lds128(rowaddr + (((k_c16 + i) ^ g) << 4));
+            kw[n][4 * i] = x.x, kw[n][4 * i + 1] = x.y, kw[n][4 * i + 2] = x.z, kw[n][4 * i + 3] = x.w;
           }
+        }
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {   // the two accumulator chains interleave
+#pragma unroll
+          for (int n = 0; n < 2; ++n)
+            mma_16816<__half>(s[n], qa[ks][0], 0u, qa[ks][1], 0u, e4m3x2_to_f16x2(kw[n][ks] & 0xffffu),
+                              e4m3x2_to_f16x2(kw[n][ks] >> 16));
         }
         // mask tokens beyond the context (only the last tile of a sequence)
         const int valid = len - tok0;  // > 0
