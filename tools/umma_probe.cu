@@ -20,6 +20,10 @@ __device__ void load_panels(uint8_t* dst, const bf16* src, int rows, int cols) {
 
 // mode 0: out[128][N] = A[128][K] * B[N][K]^T      (both K-major)
 // mode 1: out[128][N] = A[128][K] * Bmn[K][N]      (B MN-major: rows = K index, N contiguous)
+// mode 2 / 3: as 0 / 1 but A comes from TENSOR MEMORY (the ".ts" form: P of the PV product in an
+//   FA4-shaped kernel). Hypothesis under test: a 16-bit A operand [128][K] occupies K/2 32-bit
+//   columns, lane = row, column c = elements (2c, 2c+1) of that row -- written here with
+//   tcgen05.st.32x32b (thread = lane, register i = column i) from packed bf16 pairs.
 extern "C" __global__ void __launch_bounds__(128)
 umma_probe_kernel(const bf16* A, const bf16* B, float* out, int N, int K, int mode) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -30,7 +34,7 @@ umma_probe_kernel(const bf16* A, const bf16* B, float* out, int N, int K, int mo
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   load_panels(sA, A, 128, K);
-  if (mode == 0) load_panels(sB, B, N, K); else load_panels(sB, B, K, N);
+  if ((mode & 1) == 0) load_panels(sB, B, N, K); else load_panels(sB, B, K, N);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
@@ -38,14 +42,32 @@ umma_probe_kernel(const bf16* A, const bf16* B, float* out, int N, int K, int mo
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
+  const bool a_tmem = mode >= 2;
+  const int bmode = mode & 1;
+  const uint32_t ta = tb + 256 - K / 2;          // A operand columns (accumulator uses [0, N))
+  if (a_tmem) {
+    // thread = row; K/2 packed columns in chunks of 32
+    const int row = warp * 32 + (threadIdx.x & 31);
+    for (int c0 = 0; c0 < K / 2; c0 += 32) {
+      uint32_t r[32];
+      for (int i = 0; i < 32; ++i)
+        r[i] = *reinterpret_cast<const uint32_t*>(A + (size_t)row * K + 2 * (c0 + i));
+      umma::st32(ta + ((uint32_t)(warp * 32) << 16) + c0, r);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
   if (threadIdx.x == 0) {
-    const uint32_t idesc = umma::make_idesc<bf16>(128, N, 0, mode);
+    const uint32_t idesc = umma::make_idesc<bf16>(128, N, 0, bmode);
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint64_t ad = umma::desc_kmajor(smem_u32(sA) + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
       uint64_t bd;
-      if (mode == 0) bd = umma::desc_kmajor(smem_u32(sB) + (ks >> 2) * (N * 128) + (ks & 3) * 32);
-      else           bd = umma::desc_mnmajor(smem_u32(sB) + ks * 16 * 128, K * 128);
-      umma::mma_ss(tb, ad, bd, idesc, ks > 0);
+      if (bmode == 0) bd = umma::desc_kmajor(smem_u32(sB) + (ks >> 2) * (N * 128) + (ks & 3) * 32);
+      else            bd = umma::desc_mnmajor(smem_u32(sB) + ks * 16 * 128, K * 128);
+      if (a_tmem) umma::mma_ts(tb, ta + ks * 8, bd, idesc, ks > 0);   // 16 K-elements = 8 columns
+      else        umma::mma_ss(tb, ad, bd, idesc, ks > 0);
     }
     umma::commit(&bar);
   }
@@ -73,7 +95,9 @@ extern "C" int umma_probe(const void* A, const void* B, float* out, int N, int K
 // ---- throughput probe: one CTA per SM issues `reps` x (ksteps MMAs) back to back and reports the
 // cycles per MMA instruction for a given shape / operand majorness.
 extern "C" __global__ void __launch_bounds__(128)
-umma_rate_kernel(long long* cycles_out, int N, int ksteps, int b_mn, int reps) {
+umma_rate_kernel(long long* cycles_out, int N, int ksteps, int b_mn_flags, int reps) {
+  const int b_mn = b_mn_flags & 1;
+  const bool a_tmem = (b_mn_flags & 2) != 0;     // A from tensor memory (columns 448..511; content irrelevant)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -104,7 +128,10 @@ umma_rate_kernel(long long* cycles_out, int N, int ksteps, int b_mn, int reps) {
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          if (ks < ksteps) umma::mma_ss(tb + (r & 1) * 256, ad[ks], bd[ks], idesc, ks > 0);
+          if (ks < ksteps) {
+            if (a_tmem) umma::mma_ts(tb + (r & 1) * 256 * (N <= 192), tb + 448 + ks * 8, bd[ks], idesc, ks > 0);
+            else        umma::mma_ss(tb + (r & 1) * 256 * (N <= 192), ad[ks], bd[ks], idesc, ks > 0);
+          }
       }
       __syncwarp();
     }
