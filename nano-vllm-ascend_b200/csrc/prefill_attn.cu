@@ -248,13 +248,23 @@ int prefill_umma_launch(void* out, const void* q, const void* k, const void* v, 
                         int64_t v_stride, int64_t out_stride, const int32_t* block_tables,
                         int bt_stride, int num_blocks, int block_size, float scale, int dtype,
                         cudaStream_t stream);  // prefill_umma.cu
+int prefill_umma2_launch(void* out, const void* q, const void* k, const void* v, const int32_t* cu_q,
+                         const int32_t* cu_k, int num_seqs, int total_q, int total_k,
+                         int max_seqlen_q, int H, int Hkv, int D, int64_t q_stride, int64_t k_stride,
+                         int64_t v_stride, int64_t out_stride, const int32_t* block_tables,
+                         int bt_stride, int num_blocks, int block_size, float scale, int dtype,
+                         cudaStream_t stream);  // prefill_umma2.cu (opt-in)
 
-static bool use_umma() {
+// B200_PREFILL_KERNEL: unset / "umma" = prefill_umma.cu (default), "umma2" = prefill_umma2.cu
+// (opt-in until validated on hardware), "mma_sync" = the kernel in this file. Returns 1, 2, 0.
+static int prefill_kernel_choice() {
   static int v = [] {
     const char* e = getenv("B200_PREFILL_KERNEL");
-    return (e != nullptr && strcmp(e, "mma_sync") == 0) ? 0 : 1;
+    if (e != nullptr && strcmp(e, "mma_sync") == 0) return 0;
+    if (e != nullptr && strcmp(e, "umma2") == 0) return 2;
+    return 1;
   }();
-  return v != 0;
+  return v;
 }
 
 }  // namespace b200
@@ -294,11 +304,11 @@ extern "C" int b200_prefill_varlen_attn(void* out, const void* q, const void* k,
                      !aligned16(v) || (reinterpret_cast<uintptr_t>(out) & 3),
                  B200_ERR_MISALIGNED);
   cudaStream_t s = (cudaStream_t)stream;
-  if (use_umma()) {
-    const int rc = prefill_umma_launch(out, q, k, v, cu_seqlens_q, cu_seqlens_k, num_seqs, total_q,
-                                       total_k, max_seqlen_q, num_heads, num_kv_heads, head_dim,
-                                       q_stride, k_stride, v_stride, out_stride, block_tables,
-                                       block_table_stride, num_blocks, block_size, scale, dtype, s);
+  const int choice = prefill_kernel_choice();
+  if (choice != 0) {
+    const int rc = (choice == 2 ? prefill_umma2_launch : prefill_umma_launch)(out, q, k, v, cu_seqlens_q, cu_seqlens_k, num_seqs, total_q,
+        total_k, max_seqlen_q, num_heads, num_kv_heads, head_dim, q_stride, k_stride, v_stride,
+        out_stride, block_tables, block_table_stride, num_blocks, block_size, scale, dtype, s);
     if (rc != B200_ERR_UNSUPPORTED) return rc;
   }
   PrefillParams p;

@@ -1,0 +1,396 @@
+// prefill_umma2.cu -- K4/K5, second tcgen05 kernel ("FA4 shape"): 128-key S tiles and P fed to the
+// PV product straight from TENSOR MEMORY. Opt-in (B200_PREFILL_KERNEL=umma2) until it has been
+// validated on hardware; prefill_umma.cu stays the default. Same entry contract and semantics.
+//
+// Why (measured with tools/umma_probe.cu on a B200, profiles/r01_umma_probe.log): prefill_umma.cu is
+// bound by shared-memory operand traffic, not by tensor math -- per 64 keys and 128 query rows it
+// issues 8 SS-mode M128 N64 K16 MMAs (75 cycles each, smem-bandwidth bound) + 4 SS-mode N=D MMAs (107)
+// and moves every P tile through shared memory (st.shared by 128 threads, re-read by the MMA).
+// Here, per 128 keys: 8 x SS M128 N128 K16 (107) for S and 8 x TS M128 N=D K16 (74) for PV, i.e.
+// 1448 instead of 2056 issue cycles, and P never touches shared memory.
+//
+// CTA = one (sequence, head, 256 query rows): two 128-row query tiles t = 0, 1 that ping-pong.
+//   warps 0-3 / 4-7   softmax warpgroup of tile t, one thread per query row (= one TMEM lane): reads
+//                     S[t] (128 fp32 columns) with tcgen05.ld, fp32 online softmax in the exp2 domain
+//                     with lazy rescale of O (as prefill_umma.cu), writes P as packed 16-bit pairs
+//                     OVER the first 64 columns of S[t] with tcgen05.st
+//   warp 8            TMA producers: lane 0 loads Q then runs a 2-stage K ring, lane 1 a 2-stage V ring
+//                     (128-key tiles)
+//   warp 9            MMA issuer (one elected lane):
+//                       S[t]  = Q[t] K^T     8 x tcgen05.mma SS  (M128 N128 K16), K-major operands
+//                       O[t] += P[t] V       8 x tcgen05.mma TS  (M128 N=D  K16), A = P from TMEM,
+//                                            B = V MN-major straight from its [key][d] rows
+//                     issue order  S0(0) S1(0) | PV0(0) S0(1) PV1(0) S1(1) | PV0(1) S0(2) ...
+//                     so that the tensor pipe works on tile 1-t while warpgroup t is in its softmax.
+// TMEM (512 columns): O[t] at 128 t, S[t] at 256 + 128 t, P[t] aliases S[t] columns [0, 64).
+// Hazards: S[t](j+1) overwrites the columns PV[t](j) reads P from -- both are tcgen05.mma of the same
+// issuing thread and execute in issue order; softmax(j+1) of tile t starts only after S[t](j+1) has
+// completed, hence after PV[t](j) has.
+// Shared memory: Q 2 x 32 KiB + K 2 x 32 KiB + V 2 x 32 KiB = 192 KiB at D = 128.
+#include "umma.cuh"
+
+namespace b200 {
+
+struct PrefillUmma2Params {
+  const int32_t* cu_q;
+  const int32_t* cu_k;
+  const int32_t* block_tables;  // nullptr => packed K/V
+  void* out;
+  int64_t out_stride;
+  int H, G, block_size, bt_stride;
+  int kv_rows_box;   // rows per K/V TMA op (128 packed; min(block_size, 128) paged)
+  int kv_split;      // 1: each TMA op carries a single 64-wide chunk (paged, rows_box < 128)
+  float scale_log2;
+};
+
+constexpr int k2BM = 128, k2BN = 128, k2Stages = 2, k2Threads = 320;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(k2Threads, 1)
+prefill_umma2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const PrefillUmma2Params p) {
+  constexpr int CH = D / 64;                    // 128-byte chunks per head row
+  constexpr int QPANEL = k2BM * 128;            // bytes of one Q panel (128 rows)
+  constexpr int KPANEL = k2BN * 128;            // bytes of one K / V panel (128 rows)
+  constexpr int QTILE = CH * QPANEL;
+  constexpr int KTILE = CH * KPANEL;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;                            // [2][QTILE]
+  uint8_t* sK = sQ + 2 * QTILE;                  // [k2Stages][KTILE]
+  uint8_t* sV = sK + k2Stages * KTILE;           // [k2Stages][KTILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + k2Stages * KTILE);
+  uint64_t* q_full = bars;                       // [1]
+  uint64_t* k_full = bars + 1;                   // [k2Stages]
+  uint64_t* v_full = k_full + k2Stages;          // [k2Stages]
+  uint64_t* k_empty = v_full + k2Stages;         // [k2Stages] K stage consumed by both tiles' S(j)
+  uint64_t* v_empty = k_empty + k2Stages;        // [k2Stages] V stage consumed by both tiles' PV(j)
+  uint64_t* s_full = v_empty + k2Stages;         // [2 tiles]  S[t](j) landed in TMEM
+  uint64_t* p_full = s_full + 2;                 // [2 tiles]  128 softmax threads stored P[t](j)
+  uint64_t* o_full = p_full + 2;                 // [2 tiles]  PV[t](j) retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  pdl_wait();
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int q0 = p.cu_q[seq], Lq = p.cu_q[seq + 1] - q0;
+  const int k0 = p.cu_k[seq], Lk = p.cu_k[seq + 1] - k0;
+  const int m_tile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heavy (late) tiles first
+  const int m0 = m_tile * 2 * k2BM;
+  if (m0 >= Lq) return;                                       // uniform for the whole CTA
+  const int kvh = head / p.G;
+  const int off = Lk - Lq;
+  int n_tiles[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r0 = m0 + t * k2BM;
+    const int n_end = r0 < Lq ? min(Lk, r0 + k2BM + off) : 0;
+    n_tiles[t] = n_end > 0 ? (n_end + k2BN - 1) / k2BN : 0;
+  }
+  const int ntq = (m0 + k2BM < Lq) ? 2 : 1;
+  const int NT = max(n_tiles[0], n_tiles[1]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], k2BM);
+      mbar_init(&o_full[t], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) umma::tmem_alloc(tmem_slot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = *tmem_slot;
+
+  if (warp == 8) {
+    // =========================== TMA producer ===========================
+    if (lane < 2) {
+      const bool is_k = lane == 0;
+      const CUtensorMap* tm = is_k ? &tmK : &tmV;
+      tma_prefetch_desc(tm);
+      uint64_t pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      if (is_k) {
+        tma_prefetch_desc(&tmQ);
+        const uint64_t pol_stream = l2_policy_evict_first();
+        mbar_expect_tx(q_full, ntq * QTILE);
+        for (int t = 0; t < ntq; ++t)
+          tma_load_3d(sQ + t * QTILE, &tmQ, q_full, 0, q0 + m0 + t * k2BM, head * CH, pol_stream);
+      }
+      uint8_t* ring = is_k ? sK : sV;
+      uint64_t* full = is_k ? k_full : v_full;
+      uint64_t* empty = is_k ? k_empty : v_empty;
+      for (int j = 0; j < NT; ++j) {
+        const int s = j % k2Stages;
+        mbar_wait(&empty[s], ((j / k2Stages) & 1) ^ 1);
+        const int n0 = j * k2BN;
+        if (p.block_tables == nullptr) {
+          mbar_expect_tx(&full[s], KTILE);
+          tma_load_3d(ring + s * KTILE, tm, &full[s], 0, k0 + n0, kvh * CH, pol_keep);
+        } else {
+          const int rb = p.kv_rows_box;
+          const int nops = min(k2BN / rb, (Lk - n0 + rb - 1) / rb);
+          const int per_op = p.kv_split ? CH : 1;
+          const int op_bytes = rb * 128 * (p.kv_split ? 1 : CH);
+          mbar_expect_tx(&full[s], nops * per_op * op_bytes);
+          for (int o = 0; o < nops; ++o) {
+            const int tok = n0 + o * rb;
+            const int entry = tok / p.block_size;
+            const int blk = p.block_tables[(int64_t)seq * p.bt_stride + entry];
+            const int row = blk < 0 ? -(1 << 30) : blk * p.block_size + (tok - entry * p.block_size);
+            for (int c = 0; c < per_op; ++c) {
+              const int dst = (p.kv_split ? c * KPANEL : 0) + o * rb * 128;
+              tma_load_3d(ring + s * KTILE + dst, tm, &full[s], 0, row, kvh * CH + c, pol_keep);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =========================== MMA issuer ===========================
+    // Warp-uniform control flow, loop-invariant descriptor bases + compile-time offsets, one elected
+    // lane issues (as prefill_umma.cu).
+    const uint32_t idesc_s = umma::make_idesc<T>(k2BM, k2BN, 0, 0);   // S = Q K^T, both K-major
+    const uint32_t idesc_o = umma::make_idesc<T>(k2BM, D, 0, 1);      // O = P V, P from TMEM, V MN-major
+    const uint64_t qd0 = umma::desc_kmajor(smem_u32(sQ));
+    const uint64_t kd0 = umma::desc_kmajor(smem_u32(sK));
+    const uint64_t vd0 = umma::desc_mnmajor(smem_u32(sV), KPANEL);
+    const bool leader = umma::elect_one();
+    // S[t](j): the caller has waited for k_full of stage j % k2Stages
+    auto issue_s = [&](int t, int j) {
+      if (leader) {
+        const uint64_t kd = umma::desc_advance(kd0, (j % k2Stages) * KTILE);
+        const uint32_t d = tb + 256 + t * 128;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint64_t ad = umma::desc_advance(qd0, t * QTILE + (ks >> 2) * QPANEL + (ks & 3) * 32);
+          const uint64_t bd = umma::desc_advance(kd, (ks >> 2) * KPANEL + (ks & 3) * 32);
+          umma::mma_ss(d, ad, bd, idesc_s, ks > 0);
+        }
+        umma::commit(&s_full[t]);
+      }
+    };
+    mbar_wait(q_full, 0);
+    umma::fence_after_sync();
+    if (NT > 0) {
+      mbar_wait(&k_full[0], 0);
+      umma::fence_after_sync();
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (n_tiles[t] > 0) issue_s(t, 0);
+      if (leader) umma::commit(&k_empty[0]);
+      __syncwarp();
+    }
+    for (int j = 0; j < NT; ++j) {
+      const int s = j % k2Stages;
+      mbar_wait(&v_full[s], (j / k2Stages) & 1);
+      const bool more = j + 1 < NT;
+      if (more) mbar_wait(&k_full[(j + 1) % k2Stages], ((j + 1) / k2Stages) & 1);
+      umma::fence_after_sync();
+      const uint64_t vd = umma::desc_advance(vd0, s * KTILE);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (j < n_tiles[t]) {
+          mbar_wait(&p_full[t], j & 1);
+          umma::fence_after_sync();
+          if (leader) {
+            const uint32_t pa = tb + 256 + t * 128;                // P[t]: 16 keys = 8 packed columns
+#pragma unroll
+            for (int kk = 0; kk < k2BN / 16; ++kk)
+              umma::mma_ts(tb + t * 128, pa + kk * 8, umma::desc_advance(vd, kk * 16 * 128), idesc_o,
+                           (j > 0 || kk > 0) ? 1u : 0u);
+            umma::commit(&o_full[t]);
+          }
+          if (j + 1 < n_tiles[t]) issue_s(t, j + 1);               // overwrites S[t]/P[t]: after PV[t](j)
+        }
+      }
+      if (leader) {
+        umma::commit(&v_empty[s]);
+        if (more) umma::commit(&k_empty[(j + 1) % k2Stages]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== softmax warpgroups ===========================
+    const int t = warp >> 2;
+    const int nt = n_tiles[t];
+    const int row = (warp & 3) * 32 + lane;          // row inside the 128-row tile == TMEM lane
+    const int qrow = m0 + t * k2BM + row;            // row inside the sequence
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t s_addr = tb + lane_base + 256 + t * 128;
+    const uint32_t o_addr = tb + lane_base + t * 128;
+    const float sl2 = p.scale_log2;
+    constexpr float kLazy = 8.f;                     // see prefill_umma.cu: lazy rescale threshold (exp2 domain)
+    float m_ref = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      umma::fence_after_sync();
+      uint32_t sr[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) umma::ld32(s_addr + c * 32, sr[c]);
+      umma::wait_ld();
+      const int n0 = j * k2BN;
+      // mask (warp-uniform test: does this tile touch the diagonal or the end of the keys?)
+      const int warp_row0 = m0 + t * k2BM + (warp & 3) * 32;
+      if (n0 + k2BN > Lk || n0 + k2BN - 1 > warp_row0 + off) {
+        const int limit = min(Lk - 1, qrow + off) - n0;   // last visible key (tile-relative)
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c > limit) sr[c >> 5][c & 31] = 0xff800000u;   // -inf
+      }
+      float mx = __uint_as_float(sr[0][0]);
+#pragma unroll
+      for (int c = 1; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c >> 5][c & 31]));
+      const bool grow = (mx - m_ref) * sl2 > kLazy;       // also true for the first finite max
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m_ref;
+        const float alpha = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - m_new) * sl2);
+        if (j > 0) {
+          mbar_wait(&o_full[t], (j - 1) & 1);             // PV[t](j-1) landed
+          umma::fence_after_sync();
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 16) {     // 16 columns at a time: the S row stays in registers
+            uint32_t orr[16];
+            umma::ld16(o_addr + c0, orr);
+            umma::wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) orr[c] = __float_as_uint(__uint_as_float(orr[c]) * alpha);
+            umma::st16(o_addr + c0, orr);
+          }
+          umma::wait_st();
+        }
+        l_run *= alpha;
+        m_ref = m_new;
+      }
+      const float mb = m_ref == -INFINITY ? 0.f : m_ref * sl2;
+      float sum = 0.f;
+      // P(j): 128 keys -> 64 packed columns over S[t] columns [0, 64); this thread's S row is
+      // already in registers, other rows live in other TMEM lanes. Packed in place: element i of
+      // chunk 2h was consumed at iteration i/2.
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = h * 64 + 2 * i;
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c >> 5][c & 31]), sl2, -mb));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sr[(c + 1) >> 5][(c + 1) & 31]), sl2, -mb));
+          sum += e0 + e1;
+          sr[2 * h][i] = pack2<T>(e0, e1);
+        }
+        umma::st32(s_addr + h * 32, sr[2 * h]);
+      }
+      l_run += sum;
+      umma::wait_st();
+      umma::fence_before_sync();
+      mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue: O / l -> global
+    if (m0 + t * k2BM < Lq) {
+      T* orow = reinterpret_cast<T*>(p.out) + (int64_t)(q0 + qrow) * p.out_stride + (int64_t)head * D;
+      if (nt > 0) {
+        mbar_wait(&o_full[t], (nt - 1) & 1);
+        umma::fence_after_sync();
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 32) {
+          uint32_t orr[32];
+          umma::ld32(o_addr + c0, orr);
+          umma::wait_ld();
+          if (qrow < Lq) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              uint4 v;
+              v.x = pack2<T>(__uint_as_float(orr[c + 0]) * inv, __uint_as_float(orr[c + 1]) * inv);
+              v.y = pack2<T>(__uint_as_float(orr[c + 2]) * inv, __uint_as_float(orr[c + 3]) * inv);
+              v.z = pack2<T>(__uint_as_float(orr[c + 4]) * inv, __uint_as_float(orr[c + 5]) * inv);
+              v.w = pack2<T>(__uint_as_float(orr[c + 6]) * inv, __uint_as_float(orr[c + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + c0 + c) = v;
+            }
+          }
+        }
+      } else if (qrow < Lq) {
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 9) umma::tmem_dealloc(tb, 512);
+}
+
+template <typename T, int D>
+static int prefill_umma2_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                                  const PrefillUmma2Params& p, int num_seqs, int max_seqlen_q,
+                                  cudaStream_t stream) {
+  constexpr int CH = D / 64;
+  constexpr size_t smem = 1024 + 2 * CH * k2BM * 128 + 2 * k2Stages * CH * k2BN * 128 + 32 * 8 + 16;
+  auto kern = prefill_umma2_kernel<T, D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((max_seqlen_q + 2 * k2BM - 1) / (2 * k2BM), p.H, num_seqs);
+  launch_pdl(kern, grid, dim3(k2Threads), smem, stream, mq, mk, mv, p);
+  return finish_launch();
+}
+
+// Entry used by b200_prefill_varlen_attn (prefill_attn.cu) when B200_PREFILL_KERNEL=umma2. Returns
+// B200_ERR_UNSUPPORTED when the strides cannot be described by a TMA map (caller falls back to the
+// mma.sync kernel).
+int prefill_umma2_launch(void* out, const void* q, const void* k, const void* v,
+                         const int32_t* cu_q, const int32_t* cu_k, int num_seqs, int total_q,
+                         int total_k, int max_seqlen_q, int H, int Hkv, int D, int64_t q_stride,
+                         int64_t k_stride, int64_t v_stride, int64_t out_stride,
+                         const int32_t* block_tables, int bt_stride, int num_blocks, int block_size,
+                         float scale, int dtype, cudaStream_t stream) {
+  if (q_stride % 8 != 0 || out_stride % 8 != 0 || !aligned16(out)) return B200_ERR_UNSUPPORTED;
+  if (total_q <= 0) return B200_ERR_UNSUPPORTED;
+  const int CH = D / 64;
+  CUtensorMap mq, mk, mv;
+  int rc = get_panel_map(q, total_q, q_stride * 2, H * CH, k2BM, CH, dtype, &mq);
+  if (rc != B200_OK) return rc;
+  PrefillUmma2Params p;
+  p.cu_q = cu_q, p.cu_k = cu_k, p.block_tables = block_tables;
+  p.out = out, p.out_stride = out_stride;
+  p.H = H, p.G = H / Hkv, p.block_size = block_size, p.bt_stride = bt_stride;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  if (block_tables == nullptr) {
+    if (k_stride % 8 != 0 || v_stride % 8 != 0 || total_k <= 0) return B200_ERR_UNSUPPORTED;
+    p.kv_rows_box = k2BN, p.kv_split = 0;
+    rc = get_panel_map(k, total_k, k_stride * 2, Hkv * CH, k2BN, CH, dtype, &mk);
+    if (rc != B200_OK) return rc;
+    rc = get_panel_map(v, total_k, v_stride * 2, Hkv * CH, k2BN, CH, dtype, &mv);
+    if (rc != B200_OK) return rc;
+  } else {
+    if (block_size % 16 != 0 || (block_size < k2BN && k2BN % block_size != 0) ||
+        (block_size > k2BN && block_size % k2BN != 0))
+      return B200_ERR_UNSUPPORTED;
+    p.kv_rows_box = block_size < k2BN ? block_size : k2BN;
+    p.kv_split = p.kv_rows_box < k2BN ? 1 : 0;
+    const int64_t rows = (int64_t)num_blocks * block_size;
+    const int cbox = p.kv_split ? 1 : CH;
+    rc = get_panel_map(k, rows, (int64_t)Hkv * D * 2, Hkv * CH, p.kv_rows_box, cbox, dtype, &mk);
+    if (rc != B200_OK) return rc;
+    rc = get_panel_map(v, rows, (int64_t)Hkv * D * 2, Hkv * CH, p.kv_rows_box, cbox, dtype, &mv);
+    if (rc != B200_OK) return rc;
+  }
+  if (dtype == B200_DTYPE_BF16)
+    return D == 128 ? prefill_umma2_launch_t<__nv_bfloat16, 128>(mq, mk, mv, p, num_seqs, max_seqlen_q, stream)
+                    : prefill_umma2_launch_t<__nv_bfloat16, 64>(mq, mk, mv, p, num_seqs, max_seqlen_q, stream);
+  return D == 128 ? prefill_umma2_launch_t<__half, 128>(mq, mk, mv, p, num_seqs, max_seqlen_q, stream)
+                  : prefill_umma2_launch_t<__half, 64>(mq, mk, mv, p, num_seqs, max_seqlen_q, stream);
+}
+
+}  // namespace b200

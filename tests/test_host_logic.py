@@ -95,6 +95,18 @@ def test_fp8_oracle_and_fragment_map():
             E.run(D, h, G=8, valid=5, seed=2)
 
 
+def test_prefill_umma2_barrier_protocol_simulation():
+    """Randomised simulation of the mbarrier / TMEM hand-offs of prefill_umma2_kernel (producers, MMA
+    issuer, in-order tensor pipe, softmax threads): every resource holds what its consumer expects
+    and every run terminates, for all (n_tiles[0], n_tiles[1]) shapes the kernel can see."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import simulate_umma2_protocol as P
+    for n0, n1 in [(1, 0), (1, 1), (1, 2), (2, 3), (3, 3), (5, 6), (6, 0)]:
+        for seed in range(6):
+            P.Sim((n0, n1), random.Random(seed * 31 + n0 * 7 + n1)).run()
+
+
 # ------------------------------------------------------------------ front-end contract
 def test_sampling_params_and_config():
     from nanovllm import SamplingParams
