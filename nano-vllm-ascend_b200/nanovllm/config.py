@@ -82,6 +82,9 @@ class Config:
     distributed_launch: str = "spawn"  # "spawn": reference style (rank 0 spawns workers);
                                        # "env": every rank is already running (torchrun/SPMD)
     prefix_hit_prefill: bool = False   # feed only uncached prompt tokens (attention_ori semantics)
+    chunked_prefill: bool = False      # split prompts over several prefill steps when the token budget
+                                       # (max_num_batched_tokens) runs out; later chunks attend to the
+                                       # earlier ones through the paged cache
     kv_cache_dtype: str = "auto"       # "auto": the model dtype (reference behaviour); "fp8" /
                                        # "fp8_e4m3": e4m3 bytes, per-tensor scale 1.0
     device = "cuda"
@@ -90,9 +93,9 @@ class Config:
         assert self.kvcache_block_size % 16 == 0
         assert 1 <= self.tensor_parallel_size <= 8
         assert self.kv_cache_dtype in ("auto", "fp8", "fp8_e4m3"), self.kv_cache_dtype
-        if self.kv_cache_dtype != "auto" and self.prefix_hit_prefill:
-            raise ValueError("prefix_hit_prefill reads K/V back from the cache with the prefill kernel, "
-                             "which takes 16-bit caches only; use kv_cache_dtype='auto' with it")
+        if self.kv_cache_dtype != "auto" and (self.prefix_hit_prefill or self.chunked_prefill):
+            raise ValueError("prefix_hit_prefill / chunked_prefill read K/V back from the cache with the "
+                             "prefill kernel, which takes 16-bit caches only; use kv_cache_dtype='auto'")
         if self.hf_config is None:
             if os.path.isdir(self.model):
                 from transformers import AutoConfig
@@ -111,4 +114,5 @@ class Config:
             eos = eos[0] if eos else None
         if eos is not None:
             self.eos = eos
-        assert self.max_num_batched_tokens >= self.max_model_len
+        # without chunking a prompt must fit one prefill step (reference config.py)
+        assert self.chunked_prefill or self.max_num_batched_tokens >= self.max_model_len

@@ -114,6 +114,19 @@ class BlockManager:
                 self.hash_to_block_id[h] = block_id
             seq.block_table.append(block_id)
 
+    def forget_uncomputed(self, seq: Sequence, num_computed_tokens: int) -> None:
+        """Chunked prefill: ``allocate`` registered the hash of every full prompt block up front. If
+        the sequence leaves before its prefill completed, blocks past ``num_computed_tokens`` that
+        nobody else holds never received their K/V: drop their hashes so that no later prompt can
+        take them for cached content."""
+        first = num_computed_tokens // self.block_size
+        for block_id in seq.block_table[first:]:
+            block = self.blocks[block_id]
+            if block.ref_count == 1 and block.hash != NO_HASH:
+                if self.hash_to_block_id.get(block.hash) == block_id:
+                    del self.hash_to_block_id[block.hash]
+                block.update(NO_HASH, [])
+
     def deallocate(self, seq: Sequence) -> None:
         for block_id in reversed(seq.block_table):
             block = self.blocks[block_id]

@@ -89,15 +89,18 @@ class LLMEngine:
     def step(self):
         seqs, is_prefill = self.scheduler.schedule()
         token_ids = self.model_runner.call("run", seqs, is_prefill)
+        num_tokens = -len(seqs)
         if is_prefill:
             now = perf_counter()
+            num_tokens = 0
             for seq in seqs:
-                if seq.first_token_time is None:
+                start, end = seq.prefill_window or (0, len(seq))
+                num_tokens += end - start
+                if seq.first_token_time is None and end == len(seq):
                     seq.first_token_time = now
         self.scheduler.postprocess(seqs, token_ids)
         outputs = [(s.seq_id, s.completion_token_ids, s.num_prompt_tokens, s.num_cached_tokens)
                    for s in seqs if s.is_finished]
-        num_tokens = sum(len(s) for s in seqs) if is_prefill else -len(seqs)
         return outputs, num_tokens
 
     def generate(self, prompts, sampling_params, use_tqdm: bool = True) -> list[dict]:

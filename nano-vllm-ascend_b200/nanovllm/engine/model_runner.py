@@ -215,16 +215,22 @@ class ModelRunner:
         """Packed prompt tokens (model_runner.py:238-290). By default every prompt token is fed
         (the reference recomputes cached prefixes, :247-261); with ``prefix_hit_prefill`` only
         the uncached suffix is fed and attention reads K/V through the block tables
-        (attention_ori.py:65-66 semantics)."""
+        (attention_ori.py:65-66 semantics); with chunked prefill the scheduler hands every sequence
+        a ``prefill_window`` and later windows read the earlier ones the same way."""
         bs = self.block_size
-        hit = self.config.prefix_hit_prefill and any(s.num_cached_tokens for s in seqs) \
-            and all(s.block_table for s in seqs)
+        windows = [s.prefill_window for s in seqs]
+        hit = (self.config.prefix_hit_prefill and any(s.num_cached_tokens for s in seqs) or
+               any(w is not None and w[0] > 0 for w in windows)) and all(s.block_table for s in seqs)
         ids, pos, slots, cu_q, cu_k = [], [], [], [0], [0]
         max_q = max_k = 0
-        for seq in seqs:
-            n = len(seq)
-            start = min(seq.num_cached_tokens, n - 1) if hit else 0
-            ids.append(np.asarray(seq.token_ids[start:] if start else seq.token_ids, dtype=np.int64))
+        for seq, window in zip(seqs, windows):
+            # [start, n): the prompt tokens this step computes; keys visible to them: [0, n)
+            if window is not None:
+                start, n = window            # chunked prefill (scheduler._schedule_prefill_chunks)
+            else:
+                n = len(seq)
+                start = min(seq.num_cached_tokens, n - 1) if hit else 0
+            ids.append(np.asarray(seq.token_ids[start:n], dtype=np.int64))
             t = np.arange(start, n, dtype=np.int64)
             pos.append(t)
             cu_q.append(cu_q[-1] + n - start)

@@ -15,6 +15,7 @@ class Scheduler:
         self.max_num_batched_tokens = config.max_num_batched_tokens
         self.max_model_len = config.max_model_len
         self.eos = config.eos
+        self.chunked_prefill = getattr(config, "chunked_prefill", False)
         # the last physical block is the dummy slot padded graph rows write to
         # (reference scheduler.py:26-30, model_runner.py:310)
         self.block_manager = BlockManager(config.num_kvcache_blocks - 1, config.kvcache_block_size)
@@ -28,6 +29,11 @@ class Scheduler:
         self.waiting.append(seq)
 
     def schedule(self) -> tuple[list[Sequence], bool]:
+        if self.chunked_prefill:
+            batch = self._schedule_prefill_chunks()
+            if batch:
+                return batch, True
+            return self._schedule_decode(), False
         batch: list[Sequence] = []
         tokens = 0
         # 1) admit waiting prompts while the token budget and free blocks allow
@@ -43,6 +49,40 @@ class Scheduler:
             tokens += len(seq) - seq.num_cached_tokens
         if batch:
             return batch, True
+        return self._schedule_decode(), False
+
+    def _schedule_prefill_chunks(self) -> list[Sequence]:
+        """Chunked variant of step 1 (an extension; the reference admits whole prompts only). A prompt
+        takes its blocks on admission and is then computed ``prefill_window`` by window: it stays at
+        the head of ``waiting`` until the window that reaches its end has been scheduled, so nothing
+        can be admitted behind it -- and hit its not-yet-computed blocks -- before that step."""
+        batch: list[Sequence] = []
+        tokens = 0
+        while self.waiting and len(batch) < self.max_num_seqs:
+            seq = self.waiting[0]
+            if not seq.block_table:
+                if not self.block_manager.can_allocate(seq):
+                    break
+                self.block_manager.allocate(seq)
+                seq.num_computed_tokens = 0
+            n = len(seq)
+            start = max(seq.num_computed_tokens, min(seq.num_cached_tokens, n - 1))
+            room = self.max_num_batched_tokens - tokens
+            if room <= 0:
+                break
+            end = min(n, start + room)
+            seq.prefill_window = (start, end)
+            batch.append(seq)
+            tokens += end - start
+            if end < n:
+                break                       # budget exhausted; the prompt continues next step
+            self.waiting.popleft()
+            seq.status = SequenceStatus.RUNNING
+            self.running.append(seq)
+        return batch
+
+    def _schedule_decode(self) -> list[Sequence]:
+        batch: list[Sequence] = []
         # 2) one decode step for as many running sequences as fit; evict from the back on OOM
         while self.running and len(batch) < self.max_num_seqs:
             seq = self.running.popleft()
@@ -58,9 +98,10 @@ class Scheduler:
                 batch.append(seq)
         if batch:
             self.running.extendleft(reversed(batch))
-        return batch, False
+        return batch
 
     def preempt(self, seq: Sequence) -> None:
+        seq.num_computed_tokens, seq.prefill_window = 0, None
         seq.status = SequenceStatus.WAITING
         seq.finish_reason = FinishReason.PREEMPTED
         self.block_manager.deallocate(seq)
@@ -75,10 +116,18 @@ class Scheduler:
     def free_seq(self, seq: Sequence, reason: FinishReason) -> None:
         seq.status = SequenceStatus.FINISHED
         seq.finish_reason = reason
+        if self.chunked_prefill and seq.block_table and seq.num_computed_tokens < seq.num_prompt_tokens \
+                and seq.num_completion_tokens == 0:
+            self.block_manager.forget_uncomputed(seq, seq.num_computed_tokens)
         self.block_manager.deallocate(seq)
 
     def postprocess(self, seqs: list[Sequence], token_ids: list[int]) -> None:
         for seq, token_id in zip(seqs, token_ids):
+            window, seq.prefill_window = seq.prefill_window, None
+            if window is not None:
+                seq.num_computed_tokens = window[1]
+                if window[1] < len(seq):
+                    continue                # a non-final prompt chunk: its sampled token is meaningless
             seq.append_token(token_id)
             hit_eos = not seq.ignore_eos and token_id == self.eos
             out_of_room = (seq.num_completion_tokens == seq.max_tokens or

@@ -36,6 +36,10 @@ class Sequence:
         self.num_prompt_tokens = self.num_tokens
         self.num_cached_tokens = 0
         self.block_table: list[int] = []
+        # chunked prefill only: prompt tokens whose K/V are in the cache, and the [start, end) slice
+        # of the prompt the current prefill step computes (None = the whole prompt, reference behaviour)
+        self.num_computed_tokens = 0
+        self.prefill_window: tuple[int, int] | None = None
         self.temperature = sp.temperature
         self.max_tokens = sp.max_tokens
         self.ignore_eos = sp.ignore_eos
@@ -92,7 +96,7 @@ class Sequence:
     # otherwise num_blocks raises on the worker side.
     _WIRE = ("block_size", "seq_id", "num_tokens", "num_prompt_tokens", "num_cached_tokens",
              "block_table", "token_ids", "last_token", "status", "temperature", "max_tokens",
-             "ignore_eos", "greedy")
+             "ignore_eos", "greedy", "num_computed_tokens", "prefill_window")
 
     def __getstate__(self):
         return {k: getattr(self, k) for k in self._WIRE}

@@ -194,6 +194,64 @@ def test_block_manager_prefix_sharing():
     assert c.num_cached_tokens == 32
 
 
+def test_chunked_prefill_scheduling():
+    """chunked_prefill=True (extension): a prompt longer than the step's token budget is
+    computed window by window; windows tile the prompt exactly, the budget is never exceeded, nothing is
+    admitted behind a half-computed prompt, only the final window yields a token, and a prompt that
+    leaves half-way takes the hashes of its never-computed blocks with it."""
+    from types import SimpleNamespace
+    from nanovllm import SamplingParams
+    from nanovllm.engine.scheduler import Scheduler
+    from nanovllm.engine.sequence import Sequence
+    cfg = SimpleNamespace(max_num_seqs=8, max_num_batched_tokens=100, eos=-1, num_kvcache_blocks=65,
+                          kvcache_block_size=16, max_model_len=4096, chunked_prefill=True)
+    sched = Scheduler(cfg)
+    sp = SamplingParams(temperature=1.0, max_tokens=3, ignore_eos=True)
+    a = Sequence(list(range(1000, 1250)), sp, block_size=16)     # 250 tokens: 3 windows
+    b = Sequence(list(range(2000, 2030)), sp, block_size=16)     # 30 tokens
+    c = Sequence(list(range(1000, 1064)) + [5] * 20, sp, block_size=16)   # shares a's first 64 tokens
+    for s in (a, b, c):
+        sched.add(s)
+    seen = {id(a): [], id(b): [], id(c): []}
+    steps = []
+    while sched.waiting:
+        batch, is_prefill = sched.schedule()
+        assert is_prefill and batch
+        used = 0
+        for s in batch:
+            start, end = s.prefill_window
+            seen[id(s)].append((start, end))
+            used += end - start
+        assert used <= 100
+        steps.append([(len(s), s.prefill_window) for s in batch])
+        sched.postprocess(batch, [7] * len(batch))
+    # a: three windows tiling [0, 250); b rides along with a's last window; c re-uses a's 4 computed blocks
+    assert seen[id(a)] == [(0, 100), (100, 200), (200, 250)]
+    assert seen[id(b)] == [(0, 30)] and steps[2][1] == (30, (0, 30))
+    assert c.num_cached_tokens == 64 and seen[id(c)] == [(64, 84)]
+    assert len(steps[0]) == 1 and len(steps[1]) == 1           # nothing admitted behind a half-computed prompt
+    assert (len(a), len(b), len(c)) == (251, 31, 85)           # one token each, from the final windows only
+    assert all(s.num_computed_tokens == s.num_prompt_tokens for s in (a, b, c))
+    batch, is_prefill = sched.schedule()
+    assert not is_prefill and len(batch) == 3
+    # abort half-way: the uncomputed blocks must not stay in the prefix cache
+    d = Sequence(list(range(5000, 5200)), sp, request_id="d", block_size=16)
+    sched.add(d)
+    batch, _ = sched.schedule()
+    assert batch == [d] and d.prefill_window == (0, 100)
+    sched.postprocess(batch, [7])
+    assert d.num_computed_tokens == 100 and len(d) == 200
+    bm = sched.block_manager
+    registered = sum(1 for blk in d.block_table if bm.blocks[blk].hash != -1)
+    assert registered == 12                                     # allocate() registered all 12 full blocks
+    sched.abort_seq_group("d")
+    e = Sequence(list(range(5000, 5200)), sp, block_size=16)
+    sched.add(e)
+    batch, _ = sched.schedule()
+    assert batch == [e] and e.num_cached_tokens == 96           # only the 6 computed blocks count as cached
+    assert e.prefill_window == (96, 196)
+
+
 # ------------------------------------------------------------------ N>1: TP shards on gloo
 def _free_port():
     with socket.socket() as s:
