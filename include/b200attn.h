@@ -252,6 +252,22 @@ int b200_allreduce_add_rmsnorm_twoshot(void* out, void* residual, const void* we
                                        void* state, int32_t world, int32_t rank, int32_t dtype,
                                        b200_stream_t stream);
 
+/* C1 (fused), NVLS / multicast form of the two-shot kernel: the partial and gather buffers of all
+ * ranks are bound to one NVSwitch multicast object (set up by the caller -- the Python side uses
+ * torch.distributed._symmetric_memory for the allocation and the cuMulticast* binding). `mc_partial`
+ * and `mc_gather` are the MULTICAST addresses of the partial buffer this call reduces and of the
+ * gather buffer; `local_gather` is this rank's own (unicast) gather buffer. Rank r issues one
+ * multimem.ld_reduce (in-switch sum, fp32 accumulation, rounded once to dtype) and one multimem.st
+ * (in-switch broadcast) per 16 bytes of its row slice, then every rank runs the residual add +
+ * RMSNorm locally. Flags/state: as the two-shot form (same epoch sequence; forms may be mixed call
+ * by call). The in-switch summation order is unspecified: results agree with the other forms to
+ * one rounding of dtype, and are identical on every rank. */
+int b200_allreduce_add_rmsnorm_nvls(void* out, void* residual, const void* weight, float eps,
+                                    int32_t rows, int32_t hidden, const void* mc_partial,
+                                    void* mc_gather, const void* local_gather,
+                                    void* const* peer_flags, void* state, int32_t world,
+                                    int32_t rank, int32_t dtype, b200_stream_t stream);
+
 /* Set-up helpers for the peer buffers (NOT hot path: they allocate / map memory, synchronously).
  * alloc: cudaMalloc + zero; get/open_handle: CUDA IPC (64-byte handle, peer access enabled
  * lazily); all return 0 or a cudaError_t value. */

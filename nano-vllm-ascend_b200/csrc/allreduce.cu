@@ -21,6 +21,12 @@
 // buffer (writes the same amount); after a second flag barrier every rank runs the residual-add +
 // RMSNorm over all rows from its local gather buffer. NVLink bytes per rank: 2*(world-1)/world *
 // T*hidden*2 instead of (world-1) * T*hidden*2 -- 4.6 MB instead of 18 MB in that configuration.
+//
+// Multicast variant (allreduce_add_rmsnorm_nvls_kernel): the same two phases, but the buffers are
+// bound to an NVSwitch multicast object (NVLS). Phase 1 becomes ONE multimem.ld_reduce per 16 bytes
+// (the switch adds the world copies, fp32 accumulation) and ONE multimem.st (the switch replicates
+// the sum into every rank's gather buffer): 2/world of a message crosses this rank's links instead
+// of 2*(world-1)/world, and no SM spends issue slots on world-way loads and stores.
 #include "common.cuh"
 
 #include <cstring>
@@ -273,6 +279,122 @@ allreduce_add_rmsnorm_twoshot_kernel(const Ar2Params q, T* __restrict__ out, T* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// NVLS (multicast) variant of the two-shot kernel. `mc_partial` / `mc_gather` are MULTICAST addresses
+// of the partial and gather buffers (a load through them reduces over every rank's copy inside the
+// switch, a store lands in every rank's copy); `local_gather` is this rank's own gather buffer.
+// Same flags/state protocol as the two-shot kernel, same epoch sequence.
+struct ArMcParams {
+  ArParams base;                 // bufs[] unused; flags/state/world/rank as above
+  const void* mc_partial;
+  void* mc_gather;
+  const void* local_gather;
+  int rows;
+};
+
+template <typename T>
+__device__ __forceinline__ uint4 multimem_ld_reduce_add(const uint4* mc_addr);
+template <>
+__device__ __forceinline__ uint4 multimem_ld_reduce_add<__nv_bfloat16>(const uint4* mc_addr) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+template <>
+__device__ __forceinline__ uint4 multimem_ld_reduce_add<__half>(const uint4* mc_addr) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(uint4* mc_addr, const uint4& v) {
+  // the payload is opaque 16-bit pairs: the type only selects the vector width
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+allreduce_add_rmsnorm_nvls_kernel(const ArMcParams q, T* __restrict__ out, T* __restrict__ residual,
+                                  const T* __restrict__ weight, float eps, int hidden) {
+  __shared__ float red[32];
+  __shared__ uint32_t s_ticket;
+  const ArParams& p = q.base;
+  pdl_wait();
+  const uint32_t epoch = p.state[0] + 1;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[2], 1u);
+  __syncthreads();
+  if (s_ticket == 0 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: my slice of the rows -- in-switch sum, in-switch broadcast
+  const int nvec = hidden / 8;
+  const int slice = (q.rows + p.world - 1) / p.world;
+  const int row0 = min(p.rank * slice, q.rows), row1 = min(row0 + slice, q.rows);
+  const int64_t v_begin = (int64_t)row0 * nvec, v_end = (int64_t)row1 * nvec;
+  const uint4* mc_in = reinterpret_cast<const uint4*>(q.mc_partial);
+  uint4* mc_out = reinterpret_cast<uint4*>(q.mc_gather);
+  for (int64_t idx = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < v_end;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    multimem_st(mc_out + idx, multimem_ld_reduce_add<T>(mc_in + idx));
+  // ---- barrier 2: the last CTA of this rank to finish its stores tells every peer
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[3], 1u);
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + kMaxWorld + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + kMaxWorld + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: residual add + RMSNorm over all rows from the local gather buffer
+  const uint4* gathered = reinterpret_cast<const uint4*>(q.local_gather);
+  for (int row = blockIdx.x; row < q.rows; row += gridDim.x) {
+    add_rmsnorm_row<T>(row, hidden, out, residual, weight, eps, red, [&](int64_t idx, float (&acc)[8]) {
+      const uint4 y = __ldcg(gathered + idx);
+      const uint32_t w[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack2<T>(w[j]);
+        acc[2 * j] = f.x;
+        acc[2 * j + 1] = f.y;
+      }
+    });
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(&p.state[1], 1u);
+    if (done == gridDim.x - 1) {
+      p.state[1] = 0;
+      p.state[2] = 0;
+      p.state[3] = 0;
+      __threadfence();
+      p.state[0] = epoch;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -356,6 +478,52 @@ extern "C" int b200_allreduce_add_rmsnorm_twoshot(void* out, void* residual, con
     launch_pdl(allreduce_add_rmsnorm_twoshot_kernel<__half>, dim3(grid), dim3(256), 0,
                (cudaStream_t)stream, q, (__half*)out, (__half*)residual, (const __half*)weight, eps,
                hidden);
+  return finish_launch();
+}
+
+extern "C" int b200_allreduce_add_rmsnorm_nvls(void* out, void* residual, const void* weight, float eps,
+                                               int32_t rows, int32_t hidden, const void* mc_partial,
+                                               void* mc_gather, const void* local_gather,
+                                               void* const* peer_flags, void* state, int32_t world,
+                                               int32_t rank, int32_t dtype, b200_stream_t stream) {
+  B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
+  B200_RETURN_IF(rows < 0 || hidden <= 0 || world < 2 || world > kMaxWorld || rank < 0 || rank >= world,
+                 B200_ERR_BAD_SHAPE);
+  if (rows == 0) return B200_OK;
+  B200_RETURN_IF(!out || !residual || !weight || !mc_partial || !mc_gather || !local_gather ||
+                     !peer_flags || !state,
+                 B200_ERR_NULL_POINTER);
+  B200_RETURN_IF(hidden % 8 != 0 || !aligned16(out) || !aligned16(residual) || !aligned16(weight) ||
+                     !aligned16(mc_partial) || !aligned16(mc_gather) || !aligned16(local_gather),
+                 B200_ERR_MISALIGNED);
+  B200_RETURN_IF(hidden > 8 * 256 * 4, B200_ERR_UNSUPPORTED);
+  ArMcParams q;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    q.base.bufs[r] = nullptr;
+    q.base.flags[r] = nullptr;
+  }
+  for (int r = 0; r < world; ++r) {
+    B200_RETURN_IF(!peer_flags[r], B200_ERR_NULL_POINTER);
+    q.base.flags[r] = reinterpret_cast<uint32_t*>(peer_flags[r]);
+  }
+  q.base.state = reinterpret_cast<uint32_t*>(state);
+  q.base.world = world;
+  q.base.rank = rank;
+  q.mc_partial = mc_partial;
+  q.mc_gather = mc_gather;
+  q.local_gather = local_gather;
+  q.rows = rows;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int rows_per_cta = (rows + sms - 1) / sms;
+  const int grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  if (dtype == B200_DTYPE_BF16)
+    launch_pdl(allreduce_add_rmsnorm_nvls_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0,
+               (cudaStream_t)stream, q, (__nv_bfloat16*)out, (__nv_bfloat16*)residual,
+               (const __nv_bfloat16*)weight, eps, hidden);
+  else
+    launch_pdl(allreduce_add_rmsnorm_nvls_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+               q, (__half*)out, (__half*)residual, (const __half*)weight, eps, hidden);
   return finish_launch();
 }
 

@@ -7,6 +7,12 @@ fused kernel reads every rank's copy: one-shot (b200_allreduce_add_rmsnorm, ever
 copies) for small messages, two-shot (b200_allreduce_add_rmsnorm_twoshot, each rank reduces a slice
 of the rows and pushes the sums into every rank's gather buffer) for larger ones. Set-up uses
 torch.distributed only to exchange the 64-byte IPC handles.
+
+With ``B200_NVLS_ALLREDUCE=1`` the region is instead a torch symmetric-memory allocation (plumbing:
+cuMemCreate + handle exchange + cuMulticastBindMem done by ``torch.distributed._symmetric_memory``),
+which yields the same per-rank peer pointers PLUS one multicast address for the whole region; larger
+messages then go through b200_allreduce_add_rmsnorm_nvls (in-switch reduce + in-switch broadcast).
+Staged: compiled, not yet run on hardware.
 """
 from __future__ import annotations
 
@@ -37,6 +43,28 @@ class PeerAllReduce:
         self.device = device
         self.max_bytes = int(max_bytes)
         total = 3 * self.max_bytes + 2 * self.FLAG_BYTES
+        self.multicast_ptr = 0       # multicast address of the region (NVLS), 0 = not available
+        self._symm = None
+        nvls = os.environ.get("B200_NVLS_ALLREDUCE", "0")
+        if nvls != "0":
+            self._map_symmetric(total)
+        else:
+            self._map_ipc(total)
+        arr = ctypes.c_void_p * self.world
+        self._bufs = [arr(*[p + par * self.max_bytes for p in self.peer_ptrs]) for par in (0, 1)]
+        self._gather = arr(*[p + 2 * self.max_bytes for p in self.peer_ptrs])
+        self._flags = arr(*[p + 3 * self.max_bytes for p in self.peer_ptrs])
+        self._state = self.local_ptr + 3 * self.max_bytes + self.FLAG_BYTES
+        # two-shot kernel: compiled and unit-tested on 2 GPUs only when enabled; opt-in until the
+        # multi-GPU validation recorded in DESIGN.md section 6 is done
+        self.two_shot = os.environ.get("B200_TWOSHOT_ALLREDUCE", "0") == "1"
+        self.nvls_all = nvls == "all"    # tuning aid: multicast form for every message size
+        self._parity = 0
+        self.pending = None          # (tensor, parity) written by the last deferred row-parallel GEMM
+        dist.barrier()
+
+    def _map_ipc(self, total: int) -> None:
+        lib = self.lib
         ptr = ctypes.c_void_p()
         _C.check(lib.b200_comm_alloc(total, ctypes.byref(ptr)), "b200_comm_alloc")
         self.local_ptr = ptr.value
@@ -52,18 +80,24 @@ class PeerAllReduce:
                 p = ctypes.c_void_p()
                 _C.check(lib.b200_comm_open_handle(handles[r], ctypes.byref(p)), "b200_comm_open_handle")
                 self.peer_ptrs.append(p.value)
-        self.local = torch.as_tensor(_RawCudaBuffer(self.local_ptr, total), device=device)
-        arr = ctypes.c_void_p * self.world
-        self._bufs = [arr(*[p + par * self.max_bytes for p in self.peer_ptrs]) for par in (0, 1)]
-        self._gather = arr(*[p + 2 * self.max_bytes for p in self.peer_ptrs])
-        self._flags = arr(*[p + 3 * self.max_bytes for p in self.peer_ptrs])
-        self._state = self.local_ptr + 3 * self.max_bytes + self.FLAG_BYTES
-        # two-shot kernel: compiled and unit-tested on 2 GPUs only when enabled; opt-in until the
-        # multi-GPU validation recorded in DESIGN.md section 6 is done
-        self.two_shot = os.environ.get("B200_TWOSHOT_ALLREDUCE", "0") == "1"
-        self._parity = 0
-        self.pending = None          # (tensor, parity) written by the last deferred row-parallel GEMM
-        dist.barrier()
+        self.local = torch.as_tensor(_RawCudaBuffer(self.local_ptr, total), device=self.device)
+
+    def _map_symmetric(self, total: int) -> None:
+        """Region allocated and exchanged by torch symmetric memory; raises if the platform cannot
+        bind it to a multicast object (no silent downgrade: the caller asked for NVLS)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        self.local = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        self._symm = symm_mem.rendezvous(self.local, dist.group.WORLD)
+        self.local.zero_()
+        torch.cuda.synchronize(self.device)
+        self.local_ptr = self.local.data_ptr()
+        self.peer_ptrs = [int(p) for p in self._symm.buffer_ptrs]
+        if self.peer_ptrs[self.rank] != self.local_ptr:
+            raise RuntimeError("symmetric memory: local buffer pointer mismatch")
+        self.multicast_ptr = int(self._symm.multicast_ptr or 0)
+        if not self.multicast_ptr:
+            raise RuntimeError("B200_NVLS_ALLREDUCE is set but this platform offers no multicast "
+                               "(NVSwitch / driver support missing)")
 
     # one-shot: every rank pulls (world-1) full copies over NVLink; beyond a few MB of incoming
     # traffic a bandwidth-optimal algorithm (NCCL; later a row-sliced two-shot kernel) wins.
@@ -76,6 +110,9 @@ class PeerAllReduce:
         nbytes = rows * hidden * itemsize
         if nbytes > self.max_bytes or hidden % 8 != 0 or hidden > 8192:
             return None
+        if self.multicast_ptr and rows >= self.world and (
+                self.nvls_all or (self.world - 1) * nbytes > self.ONE_SHOT_MAX_INCOMING):
+            return "nvls"
         if (self.world - 1) * nbytes <= self.ONE_SHOT_MAX_INCOMING:
             return "one"
         return "two" if self.two_shot and rows >= self.world else None
@@ -101,7 +138,15 @@ class PeerAllReduce:
         self.pending = None
         rows, hidden = view.shape
         from .ops import _dt, _stream
-        if (mode or self.mode(rows, hidden, view.dtype.itemsize)) == "two":
+        mode = mode or self.mode(rows, hidden, view.dtype.itemsize)
+        if mode == "nvls":
+            mc = self.multicast_ptr
+            _C.check(self.lib.b200_allreduce_add_rmsnorm_nvls(
+                out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
+                mc + parity * self.max_bytes, mc + 2 * self.max_bytes,
+                self.local_ptr + 2 * self.max_bytes, self._flags, self._state, self.world, self.rank,
+                _dt(view), _stream()), "b200_allreduce_add_rmsnorm_nvls")
+        elif mode == "two":
             _C.check(self.lib.b200_allreduce_add_rmsnorm_twoshot(
                 out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
                 self._bufs[parity], self._gather, self._flags, self._state, self.world, self.rank,
@@ -114,6 +159,10 @@ class PeerAllReduce:
         return out, residual
 
     def close(self):
+        if self._symm is not None:        # torch owns the symmetric allocation and its mappings
+            self._symm = None
+            self.local = None
+            return
         for r, p in enumerate(self.peer_ptrs):
             if r != self.rank:
                 self.lib.b200_comm_close_handle(p)

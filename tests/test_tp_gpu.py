@@ -1,5 +1,6 @@
 """-m gpu, needs >= 2 GPUs: tensor-parallel engine (NCCL all-reduce in the row-parallel linears,
 vocab-parallel embedding / LM head gather, sampled ids broadcast) against the single-GPU engine."""
+import os
 import random
 
 import pytest
@@ -42,6 +43,10 @@ _ONE_SHOT_CASES = [(256, 1024, None), (1, 1024, None), (37, 5120, None), (256, 1
 # calls interleaved on the same flags/epoch sequence
 _TWO_SHOT_CASES = [(256, 5120, "two"), (37, 5120, "two"), (1, 1024, "two"), (8, 2048, "one"),
                    (3, 2048, "two"), (256, 1024, "two"), (5, 8192, "one"), (255, 4096, "two")]
+# NVLS / multicast form (in-switch reduce + broadcast), mixed with the other two forms on one epoch
+# sequence; rows < world falls outside its contract (mode() never selects it there)
+_NVLS_CASES = [(256, 5120, "nvls"), (37, 5120, "nvls"), (8, 2048, "one"), (2, 1024, "nvls"),
+               (256, 1024, "nvls"), (64, 2048, "two"), (255, 4096, "nvls"), (256, 8192, "nvls")]
 
 
 def _ar_worker(rank, world, port, out_q, cases):
@@ -112,3 +117,12 @@ def test_fused_peer_allreduce_twoshot_kernel():
     """b200_allreduce_add_rmsnorm_twoshot (reduce a row slice, push the sums, norm locally)."""
     _need_gpus(2)
     assert _run_ar_workers(2, 28033, _TWO_SHOT_CASES) == {0: True, 1: True}
+
+
+@pytest.mark.skipif(os.environ.get("B200_NVLS_ALLREDUCE", "0") == "0",
+                    reason="staged: needs B200_NVLS_ALLREDUCE=1 (symmetric-memory region + multicast)")
+def test_fused_peer_allreduce_nvls_kernel():
+    """b200_allreduce_add_rmsnorm_nvls (multimem.ld_reduce / multimem.st through the NVSwitch
+    multicast mapping torch symmetric memory sets up)."""
+    _need_gpus(2)
+    assert _run_ar_workers(2, 28035, _NVLS_CASES) == {0: True, 1: True}

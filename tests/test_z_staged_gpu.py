@@ -66,3 +66,13 @@ def test_chunked_prefill_engine_matches_unchunked():
     the host logic has only run on CPU)."""
     r = subprocess.run([sys.executable, "-c", _CHUNKED], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "chunked ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_nvls_allreduce_kernel_and_tp2_engine():
+    """Multicast all-reduce (comm.py `_map_symmetric`, allreduce.cu nvls kernel): kernel cases on 2
+    GPUs, then the TP=2 engine against TP=1 with every fused all-reduce forced through it."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _pytest_child(["tests/test_tp_gpu.py", "-k", "nvls"], {"B200_NVLS_ALLREDUCE": "1"}, 400)
+    _pytest_child(["tests/test_tp_gpu.py", "-k", "tp2_matches_tp1"], {"B200_NVLS_ALLREDUCE": "all"}, 600)
