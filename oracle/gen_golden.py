@@ -227,6 +227,85 @@ def gen_models():
     return out
 
 
+def moe_block_weights(E, hidden, inter, seed, dtype=torch.bfloat16):
+    """Seeded weights of one sparse-MoE block (regenerated identically by the tests, so the
+    fixture stores outputs only): router [E, h] ~ N(0, 1) (spread-out routing probabilities),
+    expert matrices ~ N(0, 0.1)."""
+    g = torch.Generator().manual_seed(seed)
+    gate = torch.randn(E, hidden, generator=g).to(dtype)
+    w13 = (0.1 * torch.randn(E, 2 * inter, hidden, generator=g)).to(dtype)
+    w2 = (0.1 * torch.randn(E, hidden, inter, generator=g)).to(dtype)
+    return gate, w13, w2
+
+
+MOE_BLOCK_CASES = {            # name: (tokens, hidden, moe_intermediate, experts, top_k, seed)
+    "e8_k2": (37, 128, 64, 8, 2, 11),
+    "e32_k4": (64, 128, 64, 32, 4, 12),
+    "e128_k8": (48, 256, 64, 128, 8, 13),
+    "single_token": (1, 128, 64, 8, 2, 14),
+}
+
+
+def gen_moe():
+    """Qwen3MoeSparseMoeBlock (models/qwen3_moe.py:125-186) and a tiny Qwen3MoeForCausalLM, both
+    the unmodified reference classes on CPU."""
+    from transformers import Qwen3MoeConfig
+    from nanovllm.models.qwen3_moe import Qwen3MoeForCausalLM, Qwen3MoeSparseMoeBlock
+    from nanovllm.layers.rotary_embedding import get_rope
+    from oracle import model_ref as M
+    from oracle import moe_ref
+    out = {}
+    old = torch.get_default_dtype()
+    for name, (T, hidden, inter, E, k, seed) in MOE_BLOCK_CASES.items():
+        hf = Qwen3MoeConfig(hidden_size=hidden, moe_intermediate_size=inter, num_experts=E,
+                            num_experts_per_tok=k, hidden_act="silu")
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            block = Qwen3MoeSparseMoeBlock(hf)
+        finally:
+            torch.set_default_dtype(old)
+        gate, w13, w2 = moe_block_weights(E, hidden, inter, seed)
+        block.gate.weight.data.copy_(gate)
+        for e, ex in enumerate(block.experts):
+            ex.gate_up_proj.weight.data.copy_(w13[e])
+            ex.down_proj.weight.data.copy_(w2[e])
+        g = torch.Generator().manual_seed(seed + 100)
+        x = torch.randn(T, hidden, generator=g).to(torch.bfloat16)
+        with torch.inference_mode():
+            y = block(x)
+        rw, ids, logits = moe_ref.route(x, gate, k)      # recorded for the kernel-level tests
+        out[name] = dict(tokens=T, hidden=hidden, inter=inter, experts=E, top_k=k, seed=seed, x=x,
+                         out=y.clone(), topk_ids=ids.to(torch.int32), topk_weights=rw, logits=logits)
+    # tiny Qwen3-MoE model, greedy
+    cfg = M.ModelCfg.tiny_qwen3_moe()
+    w = M.seeded_weights(cfg, seed=5, norm_jitter=0.1)
+    get_rope.cache_clear()
+    hf = Qwen3MoeConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
+                        num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads,
+                        num_key_value_heads=cfg.num_kv_heads, head_dim=cfg.head_dim,
+                        intermediate_size=cfg.intermediate_size,
+                        moe_intermediate_size=cfg.moe_intermediate_size, num_experts=cfg.num_experts,
+                        num_experts_per_tok=cfg.top_k, decoder_sparse_step=1, mlp_only_layers=[],
+                        rms_norm_eps=cfg.rms_eps, max_position_embeddings=cfg.max_position,
+                        tie_word_embeddings=False, attention_bias=False, hidden_act="silu")
+    torch.set_default_dtype(cfg.dtype)
+    try:
+        model = Qwen3MoeForCausalLM(hf)
+    finally:
+        torch.set_default_dtype(old)
+    params = dict(model.named_parameters())
+    assert set(params) == set(w), (set(params) ^ set(w))
+    for pname, t in w.items():
+        params[pname].data.copy_(t)
+    model.eval()
+    rnd = random.Random(3)
+    prompts = [[rnd.randint(0, cfg.vocab_size - 1) for _ in range(n)] for n in (18, 7, 33, 16)]
+    toks, logs = reference_greedy(model, cfg, prompts, 10, 16)
+    out["tiny_qwen3_moe"] = dict(seed=5, norm_jitter=0.1, prompts=prompts, max_tokens=10,
+                                 block_size=16, tokens=toks, logits=torch.stack(logs))
+    return out
+
+
 def gen_scheduler_trace():
     """Drive the reference's own Scheduler + BlockManager (engine/scheduler.py,
     engine/block_manager.py, imported unmodified) through a seeded workload that exercises
@@ -278,10 +357,13 @@ def main():
     torch.save(k, os.path.join(OUT, "kernels.pt"))
     m = gen_models()
     torch.save(m, os.path.join(OUT, "models.pt"))
+    moe = gen_moe()
+    torch.save(moe, os.path.join(OUT, "moe.pt"))
     tr = gen_scheduler_trace()
     torch.save(tr, os.path.join(OUT, "scheduler.pt"))
     print({k: len(v["steps"]) for k, v in tr.items()})
-    for name in ("kernels.pt", "models.pt", "scheduler.pt"):
+    print("tiny moe tokens", moe["tiny_qwen3_moe"]["tokens"])
+    for name in ("kernels.pt", "models.pt", "moe.pt", "scheduler.pt"):
         print(name, os.path.getsize(os.path.join(OUT, name)), "bytes")
     print("tiny tokens", m["tiny_qwen3"]["tokens"])
     print("0.6B tokens", m["qwen3_0_6b_config1"]["tokens"])

@@ -33,6 +33,17 @@ class ModelCfg:
     qk_norm: bool = True          # Qwen3 (no qkv bias) -> per-head q/k RMSNorm (qwen3.py:70-72)
     tie_embeddings: bool = True
     dtype: torch.dtype = torch.bfloat16
+    # Qwen3-MoE (models/qwen3_moe.py): num_experts > 0 makes EVERY layer's MLP a sparse MoE block
+    # (decoder_sparse_step = 1, mlp_only_layers = [] as in Qwen3-30B-A3B); intermediate_size is then unused
+    num_experts: int = 0
+    top_k: int = 0
+    moe_intermediate_size: int = 0
+
+    @staticmethod
+    def tiny_qwen3_moe():
+        return ModelCfg(vocab_size=512, hidden_size=128, num_layers=2, num_heads=4, num_kv_heads=2,
+                        head_dim=64, intermediate_size=256, num_experts=8, top_k=2,
+                        moe_intermediate_size=64, tie_embeddings=False)
 
     @staticmethod
     def qwen3_0_6b():
@@ -65,6 +76,12 @@ def param_shapes(cfg: ModelCfg) -> dict[str, tuple[int, ...]]:
         if cfg.qk_norm:
             shapes[p + "self_attn.q_norm.weight"] = (d,)
             shapes[p + "self_attn.k_norm.weight"] = (d,)
+        if cfg.num_experts:
+            shapes[p + "mlp.gate.weight"] = (cfg.num_experts, h)
+            for e in range(cfg.num_experts):
+                shapes[p + f"mlp.experts.{e}.gate_up_proj.weight"] = (2 * cfg.moe_intermediate_size, h)
+                shapes[p + f"mlp.experts.{e}.down_proj.weight"] = (h, cfg.moe_intermediate_size)
+            continue
         shapes[p + "mlp.gate_up_proj.weight"] = (2 * cfg.intermediate_size, h)
         shapes[p + "mlp.down_proj.weight"] = (h, cfg.intermediate_size)
     return shapes
@@ -138,8 +155,16 @@ def forward(w, cfg: ModelCfg, input_ids, positions, meta: StepMeta, kv_cache, bl
                                     cfg.rms_eps)
         if trace is not None:
             trace[p + "mlp_in"] = x
-        x = F.linear(x, w[p + "mlp.gate_up_proj.weight"])
-        x = F.linear(L.silu_and_mul(x), w[p + "mlp.down_proj.weight"])
+        if cfg.num_experts:      # Qwen3MoeSparseMoeBlock (qwen3_moe.py:146-186)
+            from . import moe_ref
+            x = moe_ref.sparse_moe_block(
+                x, w[p + "mlp.gate.weight"],
+                [w[p + f"mlp.experts.{e}.gate_up_proj.weight"] for e in range(cfg.num_experts)],
+                [w[p + f"mlp.experts.{e}.down_proj.weight"] for e in range(cfg.num_experts)],
+                cfg.top_k)
+        else:
+            x = F.linear(x, w[p + "mlp.gate_up_proj.weight"])
+            x = F.linear(L.silu_and_mul(x), w[p + "mlp.down_proj.weight"])
         if trace is not None:
             trace[p + "mlp_out"] = x
     x, _ = L.add_rmsnorm(x, residual, w["model.norm.weight"], cfg.rms_eps)

@@ -36,3 +36,9 @@ def golden_kernels():
 def golden_models():
     import torch
     return torch.load(os.path.join(GOLDEN, "models.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_moe():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "moe.pt"), weights_only=False)

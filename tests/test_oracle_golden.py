@@ -78,3 +78,57 @@ def test_qwen3_0_6b_config1_matches_reference(golden_models):
     top = lg.topk(8, dim=-1)
     assert torch.equal(top.indices, g["top_indices"])
     assert torch.equal(top.values, g["top_values"])
+
+
+def moe_block_weights(E, hidden, inter, seed, dtype=torch.bfloat16):
+    """Same draw as oracle/gen_golden.py::moe_block_weights (the fixture stores outputs only)."""
+    g = torch.Generator().manual_seed(seed)
+    gate = torch.randn(E, hidden, generator=g).to(dtype)
+    w13 = (0.1 * torch.randn(E, 2 * inter, hidden, generator=g)).to(dtype)
+    w2 = (0.1 * torch.randn(E, hidden, inter, generator=g)).to(dtype)
+    return gate, w13, w2
+
+
+def test_sparse_moe_block_matches_reference(golden_moe):
+    """oracle/moe_ref.py against Qwen3MoeSparseMoeBlock (models/qwen3_moe.py:125-186)."""
+    from oracle import moe_ref
+    for name in ("e8_k2", "e32_k4", "e128_k8", "single_token"):
+        g = golden_moe[name]
+        gate, w13, w2 = moe_block_weights(g["experts"], g["hidden"], g["inter"], g["seed"])
+        y = moe_ref.sparse_moe_block(g["x"], gate, w13, w2, g["top_k"])
+        assert y.dtype == torch.bfloat16 and torch.equal(y, g["out"]), name
+        rw, ids, logits = moe_ref.route(g["x"], gate, g["top_k"])
+        assert torch.equal(ids.to(torch.int32), g["topk_ids"]) and torch.equal(rw, g["topk_weights"])
+        # expert-parallel partial sums: the per-rank partials of a 2-way split add up to the full
+        # result within the roundings of the split accumulation
+        E = g["experts"]
+        parts = [moe_ref.sparse_moe_block(g["x"], gate, w13, w2, g["top_k"], experts=set(r))
+                 for r in (range(0, E // 2), range(E // 2, E))]
+        total = parts[0].float() + parts[1].float()
+        assert (total - g["out"].float()).abs().max() <= 0.02 * g["out"].float().abs().max() + 1e-3
+
+
+def test_moe_dispatch_plan_is_a_stable_sort_by_expert(golden_moe):
+    from oracle import moe_ref
+    g = golden_moe["e32_k4"]
+    ids = g["topk_ids"]
+    for begin, n in ((0, 32), (8, 8), (24, 8)):
+        offsets, sorted_pair, pos = moe_ref.dispatch_plan(ids, begin, n)
+        flat = ids.reshape(-1)
+        assert int(offsets[-1]) == len(sorted_pair) == int(((flat >= begin) & (flat < begin + n)).sum())
+        for e in range(n):
+            seg = sorted_pair[int(offsets[e]):int(offsets[e + 1])].long()
+            assert bool((flat[seg] == begin + e).all())
+            assert bool((seg[1:] > seg[:-1]).all())              # stable: ascending pair index
+        assert bool((pos[sorted_pair.long()] == torch.arange(len(sorted_pair))).all())
+        assert int((pos >= 0).sum()) == len(sorted_pair)
+
+
+def test_tiny_qwen3_moe_greedy_matches_reference(golden_moe):
+    """oracle/model_ref.py with the MoE MLP against the reference's Qwen3MoeForCausalLM."""
+    g = golden_moe["tiny_qwen3_moe"]
+    cfg = M.ModelCfg.tiny_qwen3_moe()
+    w = M.seeded_weights(cfg, seed=g["seed"], norm_jitter=g["norm_jitter"])
+    tr = M.generate_greedy(w, cfg, g["prompts"], g["max_tokens"], g["block_size"])
+    assert tr.tokens == g["tokens"]
+    assert torch.equal(torch.stack(tr.logits), g["logits"])
