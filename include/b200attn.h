@@ -220,6 +220,47 @@ int b200_sample(int64_t* out_tokens, const void* logits, const float* temperatur
                 b200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
+ * MoE  sparse mixture-of-experts MLP: routing, dispatch plan, expert GEMMs, combine.
+ * Replaces: Qwen3MoeSparseMoeBlock.forward                            models/qwen3_moe.py:146-186
+ *           (softmax/top-k :150-158, per-expert gather + Qwen3MoeMLP :95-122 + index_add_ :160-186).
+ * Expert parallelism: the caller owns experts [expert_begin, expert_begin + num_local) whole and
+ * sees every token; pairs routed elsewhere are skipped (pos_of_pair = -1) and the per-rank partial
+ * outputs are summed by the row-parallel all-reduce of the decoder layer. All buffers have fixed
+ * capacity (tokens * top_k pairs), nothing is read back by the host.
+ *
+ * b200_moe_route: router_logits [tokens, num_experts] (dtype; row stride logits_stride elements) ->
+ *   topk_ids int32 [tokens, top_k] (descending probability, ties to the lower index) and
+ *   topk_weights (dtype) = renormalised fp32 softmax probabilities. top_k <= 8, num_experts <= 256.
+ * b200_moe_align: pairs (t, j) = index t*top_k + j, stably sorted by local expert ->
+ *   offsets int32 [num_local + 1], sorted_pair int32 [num_pairs] (first offsets[num_local] valid),
+ *   pos_of_pair int32 [num_pairs] (-1 = not local); counts int32 [num_local] is scratch.
+ * b200_moe_gemm_gate_up: h[pos, :inter] = SiluAndMul(x[sorted_pair[pos] / top_k] . w13[e]^T) for the
+ *   rows pos of every local expert e; w13 [num_local, 2*inter, hidden] (gate rows, then up rows);
+ *   hidden % 64 == 0, inter % 64 == 0.
+ * b200_moe_gemm_down: y[pos, :hidden] = (h[pos] . w2[e]^T in dtype) * topk_weights[sorted_pair[pos]];
+ *   w2 [num_local, hidden, inter]; inter % 64 == 0, hidden % 128 == 0.
+ * b200_moe_combine: out[t] = sum of y[pos_of_pair[t, j]] over t's local pairs in ascending expert
+ *   order, rounded to dtype after every add (index_add_ semantics); zeros when none is local.
+ * ------------------------------------------------------------------------------- */
+int b200_moe_route(int32_t* topk_ids, void* topk_weights, const void* router_logits, int32_t tokens,
+                   int32_t num_experts, int32_t top_k, int64_t logits_stride, int32_t dtype,
+                   b200_stream_t stream);
+int b200_moe_align(int32_t* offsets, int32_t* sorted_pair, int32_t* pos_of_pair, int32_t* counts,
+                   const int32_t* topk_ids, int32_t num_pairs, int32_t expert_begin,
+                   int32_t num_local, b200_stream_t stream);
+int b200_moe_gemm_gate_up(void* h, const void* x, const void* w13, const int32_t* offsets,
+                          const int32_t* sorted_pair, int32_t hidden, int32_t inter,
+                          int32_t num_local, int32_t top_k, int64_t x_stride, int32_t dtype,
+                          b200_stream_t stream);
+int b200_moe_gemm_down(void* y, const void* h, const void* w2, const int32_t* offsets,
+                       const int32_t* sorted_pair, const void* topk_weights, int32_t inter,
+                       int32_t hidden, int32_t num_local, int32_t top_k, int32_t dtype,
+                       b200_stream_t stream);
+int b200_moe_combine(void* out, const void* y, const int32_t* topk_ids, const int32_t* pos_of_pair,
+                     int32_t tokens, int32_t top_k, int32_t hidden, int64_t out_stride,
+                     int32_t dtype, b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
  * C1 (fused)  tensor-parallel all-reduce + residual add + RMSNorm in one kernel over NVLink peer
  * memory, for decode-sized messages.
  * Replaces: dist.all_reduce(y) in RowParallelLinear.forward            layers/linear.py:151-152

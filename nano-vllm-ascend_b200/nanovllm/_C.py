@@ -55,6 +55,16 @@ PROTOTYPES = {
     "b200_add_rmsnorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,
                                    c_int32, c_void_p]),
     "b200_silu_and_mul": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "b200_moe_route": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
+                                 c_int32, c_void_p]),
+    "b200_moe_align": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                 c_int32, c_void_p]),
+    "b200_moe_gemm_gate_up": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                        c_int32, c_int32, c_int32, c_int64, c_int32, c_void_p]),
+    "b200_moe_gemm_down": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "b200_moe_combine": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                   c_int64, c_int32, c_void_p]),
     "b200_allreduce_add_rmsnorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,
                                              c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                              c_void_p]),

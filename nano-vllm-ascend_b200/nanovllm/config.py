@@ -20,7 +20,7 @@ class GraphMode(Enum):
 
 def preset_hf_config(name: str):
     """Architecture presets built offline from the public model cards."""
-    from transformers import LlamaConfig, Qwen3Config
+    from transformers import LlamaConfig, Qwen3Config, Qwen3MoeConfig
     key = name.lower().rstrip("/").split("/")[-1]
     if key == "qwen3-0.6b":
         c = Qwen3Config(vocab_size=151936, hidden_size=1024, num_hidden_layers=28,
@@ -47,9 +47,24 @@ def preset_hf_config(name: str):
                         num_attention_heads=4, num_key_value_heads=2, head_dim=64,
                         intermediate_size=512, rms_norm_eps=1e-5, max_position_embeddings=512,
                         tie_word_embeddings=True, rope_theta=10000.0)
+    elif key == "qwen3-30b-a3b":
+        c = Qwen3MoeConfig(vocab_size=151936, hidden_size=2048, num_hidden_layers=48,
+                           num_attention_heads=32, num_key_value_heads=4, head_dim=128,
+                           intermediate_size=6144, moe_intermediate_size=768, num_experts=128,
+                           num_experts_per_tok=8, decoder_sparse_step=1, mlp_only_layers=[],
+                           norm_topk_prob=True, rms_norm_eps=1e-6, max_position_embeddings=40960,
+                           tie_word_embeddings=False, attention_bias=False, rope_theta=1000000.0)
+    elif key == "tiny-qwen3-moe":
+        c = Qwen3MoeConfig(vocab_size=512, hidden_size=128, num_hidden_layers=2,
+                           num_attention_heads=4, num_key_value_heads=2, head_dim=64,
+                           intermediate_size=256, moe_intermediate_size=64, num_experts=8,
+                           num_experts_per_tok=2, decoder_sparse_step=1, mlp_only_layers=[],
+                           rms_norm_eps=1e-6, max_position_embeddings=512,
+                           tie_word_embeddings=False, attention_bias=False, rope_theta=1000000.0)
     else:
         return None
-    c.architectures = ["LlamaForCausalLM" if "llama" in key else "Qwen3ForCausalLM"]
+    c.architectures = ["LlamaForCausalLM" if "llama" in key else
+                       "Qwen3MoeForCausalLM" if isinstance(c, Qwen3MoeConfig) else "Qwen3ForCausalLM"]
     c.dtype = "bfloat16"
     c.eos_token_id = -1 if key.startswith("tiny-") else c.eos_token_id
     return c

@@ -183,7 +183,7 @@ class ModelRunner:
 
     def _allocate_kv_cache(self):
         cfg, spec = self.config, self.spec
-        kv_heads = spec.num_kv_heads // self.world_size
+        kv_heads = max(1, spec.num_kv_heads // self.world_size)    # < 1: kv heads replicated (linear.py)
         # e4m3 caches are kept as raw bytes (uint8); the attention layers dispatch on that dtype
         cache_dtype = self.dtype if cfg.kv_cache_dtype == "auto" else torch.uint8
         block_bytes = 2 * spec.num_layers * self.block_size * kv_heads * spec.head_dim * cache_dtype.itemsize

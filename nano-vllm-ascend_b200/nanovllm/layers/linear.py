@@ -102,15 +102,23 @@ class QKVParallelLinear(ColumnParallelLinear):
         total_num_kv_heads = total_num_kv_heads or total_num_heads
         self.head_size = head_size
         self.num_heads = divide(total_num_heads, tp)
-        self.num_kv_heads = divide(total_num_kv_heads, tp)
-        super().__init__(hidden_size, (total_num_heads + 2 * total_num_kv_heads) * head_size, bias)
+        # kv heads: sharded when there are at least `tp` of them, otherwise each one is replicated on
+        # tp / total consecutive ranks (one kv head per rank; an extension of the reference)
+        self.kv_replicas = 1 if total_num_kv_heads >= tp else divide(tp, total_num_kv_heads)
+        self.num_kv_heads = divide(total_num_kv_heads, tp) if self.kv_replicas == 1 else 1
+        rows = (self.num_heads + 2 * self.num_kv_heads) * head_size
+        LinearBase.__init__(self, hidden_size, rows, bias, 0)
+        self.total_num_kv_heads = total_num_kv_heads
 
     def weight_loader(self, param, loaded_weight, loaded_shard_id: str):
         q_rows = self.num_heads * self.head_size
         kv_rows = self.num_kv_heads * self.head_size
         start, size = {"q": (0, q_rows), "k": (q_rows, kv_rows), "v": (q_rows + kv_rows, kv_rows)}[
             loaded_shard_id]
-        piece = loaded_weight.chunk(self.tp_size, self.tp_dim)[self.tp_rank]
+        if loaded_shard_id == "q" or self.kv_replicas == 1:
+            piece = loaded_weight.chunk(self.tp_size, self.tp_dim)[self.tp_rank]
+        else:
+            piece = loaded_weight.chunk(self.total_num_kv_heads, self.tp_dim)[self.tp_rank // self.kv_replicas]
         param.data.narrow(self.tp_dim, start, size).copy_(piece)
 
 

@@ -50,6 +50,17 @@ class DecoderSpec:
     tie_embeddings: bool
     shared_rope: bool          # Qwen3 shares one table (lru_cache); Llama builds one per layer
     explicit_scale: bool       # Llama passes head_dim**-0.5; Qwen3 passes None (same value)
+    # sparse MoE MLPs (models/qwen3_moe.py:207-219): layer i is sparse when num_experts > 0,
+    # i is not in mlp_only_layers and (i + 1) % decoder_sparse_step == 0; dense layers use intermediate_size
+    num_experts: int = 0
+    top_k: int = 0
+    moe_intermediate_size: int = 0
+    decoder_sparse_step: int = 1
+    mlp_only_layers: tuple = ()
+
+    def is_sparse_layer(self, layer_idx: int) -> bool:
+        return (self.num_experts > 0 and layer_idx not in self.mlp_only_layers
+                and (layer_idx + 1) % self.decoder_sparse_step == 0)
 
 
 class DecoderAttention(nn.Module):
@@ -57,10 +68,13 @@ class DecoderAttention(nn.Module):
     def __init__(self, spec: DecoderSpec, rope: RotaryEmbedding):
         super().__init__()
         _, tp = tp_rank_size()
-        if spec.num_heads % tp or spec.num_kv_heads % tp:
+        if spec.num_heads % tp or (spec.num_kv_heads % tp and tp % spec.num_kv_heads):
             raise ValueError("attention heads must divide by the tensor-parallel size")
         self.num_heads = spec.num_heads // tp
-        self.num_kv_heads = spec.num_kv_heads // tp
+        # fewer kv heads than ranks (Qwen3-30B-A3B: 4 kv heads, TP=8): every kv head is replicated on
+        # tp / Hkv consecutive ranks, each rank keeps one (an extension; the reference asserts
+        # Hkv % tp == 0, qwen3_moe.py:38-39)
+        self.num_kv_heads = max(1, spec.num_kv_heads // tp)
         self.head_dim = spec.head_dim
         self.q_size = self.num_heads * self.head_dim
         self.kv_size = self.num_kv_heads * self.head_dim
@@ -114,16 +128,24 @@ class DecoderMLP(nn.Module):
 
 class DecoderLayer(nn.Module):
 
-    def __init__(self, spec: DecoderSpec, rope: RotaryEmbedding):
+    def __init__(self, spec: DecoderSpec, rope: RotaryEmbedding, layer_idx: int = 0):
         super().__init__()
         self.self_attn = DecoderAttention(spec, rope)
-        self.mlp = DecoderMLP(spec)
+        if spec.is_sparse_layer(layer_idx):
+            from ..layers.moe import SparseMoeBlock
+            self.mlp = SparseMoeBlock(spec.hidden_size, spec.moe_intermediate_size, spec.num_experts,
+                                      spec.top_k)
+        else:
+            self.mlp = DecoderMLP(spec)
         self.input_layernorm = RMSNorm(spec.hidden_size, eps=spec.rms_eps)
         self.post_attention_layernorm = RMSNorm(spec.hidden_size, eps=spec.rms_eps)
         # both row-parallel outputs of a layer feed a residual-add RMSNorm (post_attention_layernorm,
         # then the next layer's input_layernorm / the final norm): their all-reduce may be fused there
         self.self_attn.o_proj.defer_allreduce = True
-        self.mlp.down_proj.defer_allreduce = True
+        if isinstance(self.mlp, DecoderMLP):
+            self.mlp.down_proj.defer_allreduce = True
+        else:
+            self.mlp.defer_allreduce = True
 
     def forward(self, positions, hidden_states, residual):
         if residual is None:
@@ -146,8 +168,8 @@ class DecoderModel(nn.Module):
             if spec.shared_rope else None
         self.layers = nn.ModuleList([
             DecoderLayer(spec, shared if shared is not None else
-                         RotaryEmbedding(spec.head_dim, spec.head_dim, spec.max_position, spec.rope_theta))
-            for _ in range(spec.num_layers)])
+                         RotaryEmbedding(spec.head_dim, spec.head_dim, spec.max_position, spec.rope_theta), i)
+            for i in range(spec.num_layers)])
         self.norm = RMSNorm(spec.hidden_size, eps=spec.rms_eps)
 
     def forward(self, input_ids, positions):
@@ -178,6 +200,16 @@ class DecoderForCausalLM(nn.Module):
 
     def forward(self, input_ids, positions):
         return self.model(input_ids, positions)
+
+    def virtual_param_shapes(self) -> dict[str, tuple[int, ...]]:
+        """Parameters of the full model that live on OTHER ranks only (experts under expert
+        parallelism); see utils/loader.py."""
+        out = {}
+        for i, layer in enumerate(self.model.layers):
+            fn = getattr(layer.mlp, "nonlocal_param_shapes", None)
+            if fn is not None:
+                out.update(fn(f"model.layers.{i}.mlp."))
+        return out
 
     def compute_logits(self, hidden_states):
         return self.lm_head(hidden_states)

@@ -292,3 +292,85 @@ def sample(logits, temperatures=None, seed=0, step=0, out=None, step_offset=None
                                    int(step), _ptr(step_offset), _dt(logits), _stream()),
              "b200_sample")
     return out
+
+
+# ------------------------------------------------------------------ sparse MoE (csrc/moe.cu)
+class MoePlan:
+    """Device-side dispatch plan of one MoE layer call (b200_moe_align): fixed-capacity buffers,
+    nothing is read back by the host."""
+    __slots__ = ("offsets", "sorted_pair", "pos_of_pair", "counts", "num_local", "expert_begin", "top_k")
+
+    def __init__(self, num_pairs: int, num_local: int, expert_begin: int, top_k: int, device):
+        i32 = dict(dtype=torch.int32, device=device)
+        self.offsets = torch.empty(num_local + 1, **i32)
+        self.sorted_pair = torch.zeros(num_pairs, **i32)     # tail beyond offsets[-1] stays 0: never read as a row
+        self.pos_of_pair = torch.empty(num_pairs, **i32)
+        self.counts = torch.empty(num_local, **i32)
+        self.num_local, self.expert_begin, self.top_k = num_local, expert_begin, top_k
+
+
+def moe_route(router_logits: torch.Tensor, top_k: int):
+    """softmax (fp32) over all experts + top-k + renormalise (qwen3_moe.py:150-158).
+    router_logits [T, E] bf16/fp16 -> (topk_ids int32 [T, k], topk_weights dtype [T, k])."""
+    _need_cuda(router_logits)
+    T, E = router_logits.shape
+    if router_logits.stride(1) != 1:
+        raise ValueError("router_logits must be contiguous along the expert dimension")
+    ids = torch.empty(T, top_k, dtype=torch.int32, device=router_logits.device)
+    w = torch.empty(T, top_k, dtype=router_logits.dtype, device=router_logits.device)
+    _C.check(_C.load().b200_moe_route(ids.data_ptr(), w.data_ptr(), router_logits.data_ptr(), T, E, top_k,
+                                      router_logits.stride(0) if T > 1 else E, _dt(router_logits),
+                                      _stream()), "b200_moe_route")
+    return ids, w
+
+
+def moe_align(topk_ids: torch.Tensor, expert_begin: int, num_local: int) -> MoePlan:
+    """Pairs (t, j) stably sorted by local expert; see include/b200attn.h."""
+    _need_cuda(topk_ids)
+    if topk_ids.dtype != torch.int32 or not topk_ids.is_contiguous():
+        raise TypeError("topk_ids must be a contiguous int32 tensor")
+    T, k = topk_ids.shape
+    plan = MoePlan(T * k, num_local, expert_begin, k, topk_ids.device)
+    _C.check(_C.load().b200_moe_align(plan.offsets.data_ptr(), plan.sorted_pair.data_ptr(),
+                                      plan.pos_of_pair.data_ptr(), plan.counts.data_ptr(),
+                                      topk_ids.data_ptr(), T * k, expert_begin, num_local, _stream()),
+             "b200_moe_align")
+    return plan
+
+
+def moe_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_ids: torch.Tensor,
+                topk_weights: torch.Tensor, plan: MoePlan, out: torch.Tensor | None = None) -> torch.Tensor:
+    """The expert MLPs of the local experts and the per-token combine.
+    x [T, hidden]; w13 [num_local, 2*inter, hidden]; w2 [num_local, hidden, inter].
+    Returns out [T, hidden]: this rank's partial sum (the full result when it owns every expert)."""
+    _need_cuda(x, w13, w2, topk_ids, topk_weights)
+    T, hidden = x.shape
+    n_local, two_i, h2 = w13.shape
+    inter = two_i // 2
+    if h2 != hidden or w2.shape != (n_local, hidden, inter) or n_local != plan.num_local:
+        raise ValueError("expert weight shapes do not match")
+    if not (w13.is_contiguous() and w2.is_contiguous() and topk_weights.is_contiguous()):
+        raise ValueError("expert weights / routing weights must be contiguous")
+    if x.stride(1) != 1 or x.dtype != w13.dtype or x.dtype != w2.dtype or x.dtype != topk_weights.dtype:
+        raise ValueError("x must be row-major and share its dtype with the weights")
+    k = plan.top_k
+    pairs = T * k
+    lib = _C.load()
+    h = torch.empty(pairs, inter, dtype=x.dtype, device=x.device)
+    y = torch.empty(pairs, hidden, dtype=x.dtype, device=x.device)
+    _C.check(lib.b200_moe_gemm_gate_up(h.data_ptr(), x.data_ptr(), w13.data_ptr(), plan.offsets.data_ptr(),
+                                       plan.sorted_pair.data_ptr(), hidden, inter, n_local, k,
+                                       x.stride(0) if T > 1 else hidden, _dt(x), _stream()),
+             "b200_moe_gemm_gate_up")
+    _C.check(lib.b200_moe_gemm_down(y.data_ptr(), h.data_ptr(), w2.data_ptr(), plan.offsets.data_ptr(),
+                                    plan.sorted_pair.data_ptr(), topk_weights.data_ptr(), inter, hidden,
+                                    n_local, k, _dt(x), _stream()), "b200_moe_gemm_down")
+    if out is None:
+        out = torch.empty(T, hidden, dtype=x.dtype, device=x.device)
+    elif out.shape != (T, hidden) or out.dtype != x.dtype or out.stride(1) != 1:
+        raise ValueError("out must be a row-major [T, hidden] tensor of x's dtype")
+    _C.check(lib.b200_moe_combine(out.data_ptr(), y.data_ptr(), topk_ids.data_ptr(),
+                                  plan.pos_of_pair.data_ptr(), T, k, hidden,
+                                  out.stride(0) if T > 1 else hidden, _dt(x), _stream()),
+             "b200_moe_combine")
+    return out

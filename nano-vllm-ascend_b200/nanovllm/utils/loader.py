@@ -15,10 +15,18 @@ def load_model(model: nn.Module, path: str) -> int:
     fused parameter with their shard id, everything else by exact name."""
     from safetensors import safe_open
     packed = getattr(model, "packed_modules_mapping", {})
+    elsewhere = getattr(model, "virtual_param_shapes", dict)()    # experts held by other ranks
     count = 0
     for file in sorted(glob(os.path.join(path, "*.safetensors"))):
         with safe_open(file, "pt", "cpu") as f:
             for name in f.keys():
+                fused_name = name
+                for key, (fused, _) in packed.items():
+                    if key in name:
+                        fused_name = name.replace(key, fused)
+                        break
+                if fused_name in elsewhere:
+                    continue
                 tensor = f.get_tensor(name)
                 for key, (fused, shard_id) in packed.items():
                     if key in name:
@@ -42,7 +50,10 @@ def full_shapes(model: nn.Module, tp_size: int) -> dict[str, tuple[int, ...]]:
         tp_dim = getattr(mod, "tp_dim", 0 if hasattr(mod, "vocab_start_idx") else None)
         if tp_size > 1 and tp_dim is not None and len(shape) > tp_dim and not (
                 len(shape) == 1 and tp_dim == 1):
-            shape[tp_dim] *= tp_size
+            if getattr(mod, "kv_replicas", 1) > 1:     # q sharded, kv heads replicated (linear.py)
+                shape[tp_dim] = (mod.num_heads * tp_size + 2 * mod.total_num_kv_heads) * mod.head_size
+            else:
+                shape[tp_dim] *= tp_size
         shapes[name] = tuple(shape)
     return shapes
 
@@ -75,10 +86,16 @@ def seeded_init(model: nn.Module, seed: int = 0, norm_jitter: float = 0.0, std: 
     from ..layers.linear import tp_rank_size
     _, tp = tp_rank_size()
     tied = getattr(getattr(model, "spec", None), "tie_embeddings", False)
-    names = sorted(n for n, _ in model.named_parameters() if not (tied and n == "lm_head.weight"))
+    # numbered over the FULL parameter list (experts of other ranks included) so that every
+    # parallel layout draws the same weights as the single-GPU model and the oracle
+    elsewhere = getattr(model, "virtual_param_shapes", dict)()
+    names = sorted({n for n, _ in model.named_parameters() if not (tied and n == "lm_head.weight")}
+                   | set(elsewhere))
     shapes = full_shapes(model, tp)
     params = dict(model.named_parameters())
     for idx, name in enumerate(names):
+        if name in elsewhere:
+            continue
         gen = torch.Generator().manual_seed(seed * 1000003 + idx)
         shape = shapes[name]
         if len(shape) == 1:
@@ -107,7 +124,7 @@ def _load_fused(model, name, p, full):
             off += n
     elif hasattr(mod, "num_kv_heads") and hasattr(mod, "head_size"):   # q|k|v
         q = mod.num_heads * tp * mod.head_size
-        kv = mod.num_kv_heads * tp * mod.head_size
+        kv = getattr(mod, "total_num_kv_heads", mod.num_kv_heads * tp) * mod.head_size
         p.weight_loader(p, full.narrow(0, 0, q), "q")
         p.weight_loader(p, full.narrow(0, q, kv), "k")
         p.weight_loader(p, full.narrow(0, q + kv, kv), "v")

@@ -345,3 +345,109 @@ def test_seeded_init_matches_oracle_weights():
     for name, w in want.items():
         assert torch.equal(got[name].data, w), name
     assert model.lm_head.weight.data_ptr() == model.model.embed_tokens.weight.data_ptr()
+
+
+# ------------------------------------------------------------------ Qwen3-MoE: host side
+def _build_tiny_moe(tp=None, seed=None):
+    """Tiny Qwen3-MoE on CPU, optionally as rank tp[0] of tp[1], optionally seeded-initialised
+    (the initialiser needs the same tensor-parallel view as the constructor)."""
+    from nanovllm.config import preset_hf_config
+    from nanovllm.layers.linear import set_tp_world
+    from nanovllm.models.qwen3_moe import Qwen3MoeForCausalLM
+    from nanovllm.utils.loader import seeded_init
+    prev = torch.get_default_dtype()
+    try:
+        if tp is not None:
+            set_tp_world(*tp)
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            model = Qwen3MoeForCausalLM(preset_hf_config("tiny-qwen3-moe"))
+        finally:
+            torch.set_default_dtype(prev)       # the initialiser draws in fp32, like the runner
+        if seed is not None:
+            seeded_init(model, seed=seed, norm_jitter=0.1)
+        return model
+    finally:
+        set_tp_world(None)
+
+
+def test_moe_model_parameters_and_seeded_init_match_oracle():
+    """Reference parameter names (qwen3_moe.py) over stacked expert storage; the seeded initialiser
+    fills the stacks exactly as the oracle's per-expert weights."""
+    from oracle import model_ref as M
+    from nanovllm.utils.loader import seeded_init
+    cfg = M.ModelCfg.tiny_qwen3_moe()
+    model = _build_tiny_moe()
+    want = M.seeded_weights(cfg, seed=5, norm_jitter=0.1)
+    got = dict(model.named_parameters())
+    assert set(got) == set(want)
+    seeded_init(model, seed=5, norm_jitter=0.1)
+    for name, w in want.items():
+        assert torch.equal(got[name].data, w), name
+    moe = model.model.layers[1].mlp
+    for e in range(cfg.num_experts):        # the kernels read the stacks, not the per-expert views
+        assert torch.equal(moe.w13[e], want[f"model.layers.1.mlp.experts.{e}.gate_up_proj.weight"])
+        assert torch.equal(moe.w2[e], want[f"model.layers.1.mlp.experts.{e}.down_proj.weight"])
+    # checkpoint-style loading: gate_proj / up_proj halves routed by the packed-module mapping
+    p = got["model.layers.0.mlp.experts.3.gate_up_proj.weight"]
+    half = torch.full((cfg.moe_intermediate_size, cfg.hidden_size), 2.0, dtype=torch.bfloat16)
+    p.weight_loader(p, half, 1)
+    blk = model.model.layers[0].mlp
+    assert bool((blk.w13[3, cfg.moe_intermediate_size:] == 2).all())
+    assert torch.equal(blk.w13[3, :cfg.moe_intermediate_size],
+                       want["model.layers.0.mlp.experts.3.gate_up_proj.weight"][:cfg.moe_intermediate_size])
+
+
+def test_moe_expert_parallel_layout_and_kv_head_replication():
+    """tp=4 over the tiny MoE model (8 experts, 4 q heads, 2 kv heads): each rank owns 2 whole experts
+    with the weights the single-rank model has for them, and one kv head replicated on 2 ranks."""
+    from oracle import model_ref as M
+    from nanovllm.utils.loader import seeded_init
+    cfg = M.ModelCfg.tiny_qwen3_moe()
+    want = M.seeded_weights(cfg, seed=5, norm_jitter=0.1)
+    D = cfg.head_dim
+    for rank in range(4):
+        model = _build_tiny_moe(tp=(rank, 4), seed=5)
+        blk = model.model.layers[0].mlp
+        assert (blk.num_local, blk.expert_begin) == (2, 2 * rank)
+        assert sorted(blk.experts.keys()) == [str(2 * rank), str(2 * rank + 1)]
+        virtual = model.virtual_param_shapes()
+        assert len(virtual) == 2 * 2 * 6 and not (set(virtual) & set(dict(model.named_parameters())))
+        for i in range(2):
+            e = 2 * rank + i
+            assert torch.equal(blk.w13[i], want[f"model.layers.0.mlp.experts.{e}.gate_up_proj.weight"])
+            assert torch.equal(blk.w2[i], want[f"model.layers.0.mlp.experts.{e}.down_proj.weight"])
+        assert torch.equal(blk.gate.weight.data, want["model.layers.0.mlp.gate.weight"])
+        attn = model.model.layers[0].self_attn
+        assert (attn.num_heads, attn.num_kv_heads, attn.qkv_proj.kv_replicas) == (1, 1, 2)
+        full = want["model.layers.0.self_attn.qkv_proj.weight"]
+        q, k, v = full.split([cfg.num_heads * D, cfg.num_kv_heads * D, cfg.num_kv_heads * D])
+        kv = rank // 2
+        mine = torch.cat([q[rank * D:(rank + 1) * D], k[kv * D:(kv + 1) * D], v[kv * D:(kv + 1) * D]])
+        assert torch.equal(attn.qkv_proj.weight.data, mine)
+
+
+def test_moe_entry_points_reject_bad_arguments():
+    from nanovllm import _C
+    lib = _C.load()
+    one = ctypes.c_void_p(16)
+    assert lib.b200_moe_route(one, one, one, 4, 128, 9, 128, 0, None) == -3          # top_k > 8
+    assert lib.b200_moe_route(one, one, one, 4, 512, 8, 512, 0, None) == -3          # > 256 experts
+    assert lib.b200_moe_route(one, one, one, 4, 8, 9, 8, 0, None) == -2              # top_k > experts
+    assert lib.b200_moe_route(None, one, one, 4, 8, 2, 8, 0, None) == -1
+    assert lib.b200_moe_align(one, one, one, one, one, 8, 0, 0, None) == -2
+    assert lib.b200_moe_gemm_gate_up(one, one, one, one, one, 100, 64, 4, 2, 100, 0, None) == -3   # K % 64
+    assert lib.b200_moe_gemm_gate_up(one, one, one, one, one, 128, 96, 4, 2, 128, 0, None) == -3   # inter % 64
+    assert lib.b200_moe_gemm_down(one, one, one, one, one, one, 64, 192, 4, 2, 0, None) == -3      # hidden % 128
+    assert lib.b200_moe_gemm_down(one, one, one, one, one, None, 64, 128, 4, 2, 0, None) == -1
+    assert lib.b200_moe_combine(one, one, one, one, 4, 2, 100, 100, 0, None) == -4                 # hidden % 8
+    assert lib.b200_moe_combine(one, one, one, one, 0, 2, 128, 128, 0, None) == 0                  # empty batch
+
+
+def test_moe_kernel_index_emulation():
+    """tools/emulate_moe_kernels.py: thread-level transcription of the align / expert-GEMM / combine
+    index arithmetic against the oracle (the part of moe.cu a CPU can check)."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emulate_moe_kernels.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("ok ") >= 10, r.stdout[-2000:] + r.stderr[-2000:]

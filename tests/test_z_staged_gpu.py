@@ -76,3 +76,8 @@ def test_nvls_allreduce_kernel_and_tp2_engine():
         pytest.skip("needs 2 GPUs")
     _pytest_child(["tests/test_tp_gpu.py", "-k", "nvls"], {"B200_NVLS_ALLREDUCE": "1"}, 400)
     _pytest_child(["tests/test_tp_gpu.py", "-k", "tp2_matches_tp1"], {"B200_NVLS_ALLREDUCE": "all"}, 600)
+
+
+def test_moe_kernels_and_engine():
+    """csrc/moe.cu + layers/moe.py + models/qwen3_moe.py: tests/test_z_moe_gpu.py."""
+    _pytest_child(["tests/test_z_moe_gpu.py"], {"B200_RUN_MOE": "1"}, 900)
