@@ -280,7 +280,8 @@ def main():
 
     dbg(rank, 'replay done')
     # ---- phase 4: the dominant kernel alone, all layers' caches (cold in L2), CUDA events
-    Hq, Hkv, D = spec.num_heads // (world if args.tp else 1), spec.num_kv_heads // (world if args.tp else 1), spec.head_dim
+    tpw = world if args.tp else 1
+    Hq, Hkv, D = spec.num_heads // tpw, max(1, spec.num_kv_heads // tpw), spec.head_dim
     q = torch.randn(B, Hq, D, device="cuda", dtype=runner.dtype)
     o = torch.empty(B, Hq * D, device="cuda", dtype=runner.dtype)
     ws = ops.decode_workspace(B, Hq, Hkv, D, q.device)
