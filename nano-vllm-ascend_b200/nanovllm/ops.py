@@ -303,7 +303,7 @@ class MoePlan:
     def __init__(self, num_pairs: int, num_local: int, expert_begin: int, top_k: int, device):
         i32 = dict(dtype=torch.int32, device=device)
         self.offsets = torch.empty(num_local + 1, **i32)
-        self.sorted_pair = torch.zeros(num_pairs, **i32)     # tail beyond offsets[-1] stays 0: never read as a row
+        self.sorted_pair = torch.empty(num_pairs, **i32)     # only [0, offsets[-1]) is ever written or read
         self.pos_of_pair = torch.empty(num_pairs, **i32)
         self.counts = torch.empty(num_local, **i32)
         self.num_local, self.expert_begin, self.top_k = num_local, expert_begin, top_k
