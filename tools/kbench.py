@@ -1,5 +1,10 @@
 """Developer micro-benchmark of single kernels (not the contract bench; see bench.py).
-usage: python tools/kbench.py [decode|prefill|all] [--bs 16]"""
+usage: python tools/kbench.py [decode|prefill|fa2|all]
+
+`fa2` times the reference's CUDA attention variant (layers/attention_ori.py:63-74: flash_attn 2.8.3
+flash_attn_with_kvcache / flash_attn_varlen_func, library code) on the same shapes -- the
+"kernel to beat" of SURVEY.md 8(d). FA2's paged path needs page_block_size % 256 == 0, so it runs
+at block 256 (the reference default); ours is timed at block 16 and 256."""
 import argparse
 import json
 import os
@@ -80,6 +85,42 @@ def bench_prefill_prefix_hit(qlen, klen, H, G, D, bs):
                 TFLOPs_med=round(flops / med / 1e9, 1))
 
 
+def bench_fa2_decode(B, H, G, D, ctx, bs=256):
+    """attention_ori.py:72-74 -- flash_attn_with_kvcache over a paged cache."""
+    from flash_attn import flash_attn_with_kvcache
+    g = torch.Generator(device="cuda").manual_seed(0)
+    per = (ctx + bs - 1) // bs
+    nblk = B * per
+    kc = torch.randn(nblk + 1, bs, G, D, device="cuda", generator=g).to(torch.bfloat16)
+    vc = torch.randn(nblk + 1, bs, G, D, device="cuda", generator=g).to(torch.bfloat16)
+    q = torch.randn(B, 1, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    bt = torch.randperm(nblk, device="cuda", generator=g).to(torch.int32).view(B, per).contiguous()
+    cl = torch.full((B,), ctx, dtype=torch.int32, device="cuda")
+    fn = lambda: flash_attn_with_kvcache(q, kc, vc, cache_seqlens=cl, block_table=bt,
+                                         softmax_scale=D ** -0.5, causal=True)
+    med, best = timeit(fn)
+    byts = B * ctx * 2 * G * D * 2
+    return dict(kernel="fa2_with_kvcache", B=B, H=H, G=G, D=D, bs=bs, ctx=ctx, ms_med=round(med, 4),
+                GBps_med=round(byts / med / 1e6, 1), GBps_best=round(byts / best / 1e6, 1))
+
+
+def bench_fa2_prefill(nseq, L, H, G, D):
+    """attention_ori.py:67-70 -- flash_attn_varlen_func, causal, packed K/V."""
+    from flash_attn import flash_attn_varlen_func
+    g = torch.Generator(device="cuda").manual_seed(0)
+    T = nseq * L
+    q = torch.randn(T, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    k = torch.randn(T, G, D, device="cuda", generator=g).to(torch.bfloat16)
+    v = torch.randn(T, G, D, device="cuda", generator=g).to(torch.bfloat16)
+    cu = torch.arange(0, T + 1, L, dtype=torch.int32, device="cuda")
+    fn = lambda: flash_attn_varlen_func(q, k, v, max_seqlen_q=L, cu_seqlens_q=cu, max_seqlen_k=L,
+                                        cu_seqlens_k=cu, softmax_scale=D ** -0.5, causal=True)
+    med, best = timeit(fn, iters=10, warmup=3)
+    flops = 2 * L * L * H * D * nseq
+    return dict(kernel="fa2_varlen", nseq=nseq, L=L, H=H, G=G, D=D, ms_med=round(med, 4),
+                TFLOPs_med=round(flops / med / 1e9, 1), TFLOPs_best=round(flops / best / 1e9, 1))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -97,5 +138,14 @@ if __name__ == "__main__":
         res.append(bench_prefill(16, 1024, 16, 8, 128))
         res.append(bench_prefill(1, 8192, 32, 8, 64))
         res.append(bench_prefill_prefix_hit(256, 8192, 32, 8, 64, 16))
+    if args.what in ("fa2", "all"):
+        try:
+            res.append(bench_fa2_decode(256, 16, 8, 128, 1024))
+            res.append(bench_fa2_decode(256, 8, 1, 128, 1024))
+            res.append(bench_fa2_decode(256, 32, 8, 64, 1024))
+            res.append(bench_fa2_prefill(16, 1024, 16, 8, 128))
+            res.append(bench_fa2_prefill(1, 8192, 32, 8, 64))
+        except Exception as e:                     # the comparator is optional library code
+            res.append(dict(kernel="fa2", unavailable=f"{type(e).__name__}: {e}"[:200]))
     for r in res:
         print(json.dumps(r))
