@@ -6,6 +6,8 @@ are safe inside CUDA-graph capture.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _C
@@ -303,7 +305,7 @@ class MoePlan:
     def __init__(self, num_pairs: int, num_local: int, expert_begin: int, top_k: int, device):
         i32 = dict(dtype=torch.int32, device=device)
         self.offsets = torch.empty(num_local + 1, **i32)
-        self.sorted_pair = torch.empty(num_pairs, **i32)     # only [0, offsets[-1]) is ever written or read
+        self.sorted_pair = torch.zeros(num_pairs, **i32)     # tail beyond offsets[-1] stays 0 (a valid pair index)
         self.pos_of_pair = torch.empty(num_pairs, **i32)
         self.counts = torch.empty(num_local, **i32)
         self.num_local, self.expert_begin, self.top_k = num_local, expert_begin, top_k
@@ -356,6 +358,9 @@ def moe_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_ids: 
     k = plan.top_k
     pairs = T * k
     lib = _C.load()
+    if _MOE_LIBRARY_GEMM_ROWS and pairs >= _MOE_LIBRARY_GEMM_ROWS * n_local:
+        y = _moe_expert_gemms_library(x, w13, w2, topk_weights, plan)
+        return _moe_combine(lib, y, topk_ids, plan, T, hidden, out, x)
     h = torch.empty(pairs, inter, dtype=x.dtype, device=x.device)
     y = torch.empty(pairs, hidden, dtype=x.dtype, device=x.device)
     _C.check(lib.b200_moe_gemm_gate_up(h.data_ptr(), x.data_ptr(), w13.data_ptr(), plan.offsets.data_ptr(),
@@ -365,6 +370,29 @@ def moe_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_ids: 
     _C.check(lib.b200_moe_gemm_down(y.data_ptr(), h.data_ptr(), w2.data_ptr(), plan.offsets.data_ptr(),
                                     plan.sorted_pair.data_ptr(), topk_weights.data_ptr(), inter, hidden,
                                     n_local, k, _dt(x), _stream()), "b200_moe_gemm_down")
+    return _moe_combine(lib, y, topk_ids, plan, T, hidden, out, x)
+
+
+# Prefill-sized batches (hundreds of rows per expert) are tensor-bound, not weight-streaming; until
+# the tcgen05 grouped GEMM lands they may be routed to the library grouped GEMM (torch._grouped_mm)
+# around our gather / SiluAndMul / combine kernels: B200_MOE_LIBRARY_GEMM_ROWS=<avg rows per local
+# expert from which to switch>, 0 (default) = always the hand-written weight-streaming kernel.
+_MOE_LIBRARY_GEMM_ROWS = int(os.environ.get("B200_MOE_LIBRARY_GEMM_ROWS", "0"))
+
+
+def _moe_expert_gemms_library(x, w13, w2, topk_weights, plan: MoePlan) -> torch.Tensor:
+    k = plan.top_k
+    pair = plan.sorted_pair.long()                    # tail entries are 0: harmless rows, never combined
+    xs = x.index_select(0, pair // k)                 # [pairs, hidden] in expert order
+    offs = plan.offsets[1:]
+    gu = torch._grouped_mm(xs, w13.transpose(1, 2), offs=offs)
+    h = silu_and_mul(gu)
+    y = torch._grouped_mm(h, w2.transpose(1, 2), offs=offs)
+    return y * topk_weights.reshape(-1)[pair].unsqueeze(1)      # dtype multiply, as qwen3_moe.py:180-182
+
+
+def _moe_combine(lib, y, topk_ids, plan: MoePlan, T, hidden, out, x):
+    k = plan.top_k
     if out is None:
         out = torch.empty(T, hidden, dtype=x.dtype, device=x.device)
     elif out.shape != (T, hidden) or out.dtype != x.dtype or out.stride(1) != 1:

@@ -202,3 +202,25 @@ def test_tiny_qwen3_moe_cuda_graph_equals_eager():
         outs.append([o["token_ids"] for o in llm.generate(prompts, sp, use_tqdm=False)])
         llm.exit()
     assert outs[0] == outs[1]
+
+
+def test_library_grouped_gemm_path_matches_the_kernel_path(monkeypatch):
+    """B200_MOE_LIBRARY_GEMM_ROWS: prefill-sized batches through torch._grouped_mm (library GEMM)
+    around our gather / SiluAndMul / combine kernels must agree with the hand-written expert GEMMs."""
+    from nanovllm import ops
+    g = torch.Generator().manual_seed(9)
+    bf = torch.bfloat16
+    T, k, E, hidden, inter = 1500, 4, 8, 256, 128
+    x = torch.randn(T, hidden, generator=g).to(bf).cuda()
+    w13 = (hidden ** -0.5 * torch.randn(E, 2 * inter, hidden, generator=g)).to(bf).cuda()
+    w2 = (inter ** -0.5 * torch.randn(E, hidden, inter, generator=g)).to(bf).cuda()
+    ids = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(T)]).to(torch.int32).cuda()
+    w = torch.rand(T, k, generator=g)
+    w = (w / w.sum(-1, keepdim=True)).to(bf).cuda()
+    for begin, n in ((0, E), (4, 4)):
+        plan = ops.moe_align(ids, begin, n)
+        monkeypatch.setattr(ops, "_MOE_LIBRARY_GEMM_ROWS", 0)
+        a = ops.moe_experts(x, w13[begin:begin + n].contiguous(), w2[begin:begin + n].contiguous(), ids, w, plan)
+        monkeypatch.setattr(ops, "_MOE_LIBRARY_GEMM_ROWS", 64)
+        b = ops.moe_experts(x, w13[begin:begin + n].contiguous(), w2[begin:begin + n].contiguous(), ids, w, plan)
+        _close(b, a, f"library vs kernel, experts [{begin},{begin + n})")
