@@ -260,6 +260,23 @@ int b200_moe_combine(void* out, const void* y, const int32_t* topk_ids, const in
                      int32_t tokens, int32_t top_k, int32_t hidden, int64_t out_stride,
                      int32_t dtype, b200_stream_t stream);
 
+/* MoE expert GEMMs for prefill-sized batches on tcgen05 / TMEM (csrc/moe_umma.cu; staged). Same plan,
+ * rounding points and outputs as b200_moe_gemm_gate_up / _down, for hundreds of rows per expert:
+ * 128-row x 128-weight-row tiles of one expert, TMA-staged SW128 panels, accumulators in TMEM.
+ * b200_moe_gather_rows writes xs[pos, :hidden] = x[sorted_pair[pos] / top_k] for pos < offsets[num_local]
+ * (TMA needs contiguous A rows); xs / h / y have `pairs` = tokens * top_k rows of capacity.
+ * hidden % 64 == 0, inter % 64 == 0; down additionally hidden % 128 == 0. */
+int b200_moe_gather_rows(void* xs, const void* x, const int32_t* offsets, const int32_t* sorted_pair,
+                         int32_t pairs, int32_t num_local, int32_t top_k, int32_t hidden,
+                         int64_t x_stride, int32_t dtype, b200_stream_t stream);
+int b200_moe_gemm_gate_up_umma(void* h, const void* xs, const void* w13, const int32_t* offsets,
+                               int32_t pairs, int32_t hidden, int32_t inter, int32_t num_local,
+                               int32_t dtype, b200_stream_t stream);
+int b200_moe_gemm_down_umma(void* y, const void* h, const void* w2, const int32_t* offsets,
+                            const int32_t* sorted_pair, const void* topk_weights, int32_t pairs,
+                            int32_t inter, int32_t hidden, int32_t num_local, int32_t dtype,
+                            b200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------
  * C1 (fused)  tensor-parallel all-reduce + residual add + RMSNorm in one kernel over NVLink peer
  * memory, for decode-sized messages.

@@ -63,6 +63,12 @@ PROTOTYPES = {
                                         c_int32, c_int32, c_int32, c_int64, c_int32, c_void_p]),
     "b200_moe_gemm_down": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "b200_moe_gather_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                       c_int32, c_int64, c_int32, c_void_p]),
+    "b200_moe_gemm_gate_up_umma": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                             c_int32, c_int32, c_int32, c_void_p]),
+    "b200_moe_gemm_down_umma": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "b200_moe_combine": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                    c_int64, c_int32, c_void_p]),
     "b200_allreduce_add_rmsnorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,

@@ -358,8 +358,9 @@ def moe_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_ids: 
     k = plan.top_k
     pairs = T * k
     lib = _C.load()
-    if _MOE_LIBRARY_GEMM_ROWS and pairs >= _MOE_LIBRARY_GEMM_ROWS * n_local:
-        y = _moe_expert_gemms_library(x, w13, w2, topk_weights, plan)
+    if _MOE_BIG_GEMM and pairs >= _MOE_BIG_GEMM_ROWS * n_local:
+        big = _moe_expert_gemms_umma if _MOE_BIG_GEMM == "umma" else _moe_expert_gemms_library
+        y = big(x, w13, w2, topk_weights, plan)
         return _moe_combine(lib, y, topk_ids, plan, T, hidden, out, x)
     h = torch.empty(pairs, inter, dtype=x.dtype, device=x.device)
     y = torch.empty(pairs, hidden, dtype=x.dtype, device=x.device)
@@ -373,11 +374,35 @@ def moe_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_ids: 
     return _moe_combine(lib, y, topk_ids, plan, T, hidden, out, x)
 
 
-# Prefill-sized batches (hundreds of rows per expert) are tensor-bound, not weight-streaming; until
-# the tcgen05 grouped GEMM lands they may be routed to the library grouped GEMM (torch._grouped_mm)
-# around our gather / SiluAndMul / combine kernels: B200_MOE_LIBRARY_GEMM_ROWS=<avg rows per local
-# expert from which to switch>, 0 (default) = always the hand-written weight-streaming kernel.
-_MOE_LIBRARY_GEMM_ROWS = int(os.environ.get("B200_MOE_LIBRARY_GEMM_ROWS", "0"))
+# Prefill-sized batches (hundreds of rows per expert) are tensor-bound, not weight-streaming.
+# B200_MOE_BIG_GEMM selects what serves them: "" (default) = the weight-streaming kernel for every size
+# (validated path first), "umma" = the tcgen05 grouped GEMM of csrc/moe_umma.cu, "library" =
+# torch._grouped_mm around our gather / SiluAndMul / combine kernels (comparator). The switch happens at
+# B200_MOE_BIG_GEMM_ROWS average rows per local expert.
+_MOE_BIG_GEMM = os.environ.get("B200_MOE_BIG_GEMM", "")
+_MOE_BIG_GEMM_ROWS = int(os.environ.get("B200_MOE_BIG_GEMM_ROWS", "96"))
+
+
+def _moe_expert_gemms_umma(x, w13, w2, topk_weights, plan: MoePlan) -> torch.Tensor:
+    T, hidden = x.shape
+    n_local, two_i, _ = w13.shape
+    inter, k = two_i // 2, plan.top_k
+    pairs = T * k
+    lib = _C.load()
+    xs = torch.empty(pairs, hidden, dtype=x.dtype, device=x.device)
+    h = torch.empty(pairs, inter, dtype=x.dtype, device=x.device)
+    y = torch.empty(pairs, hidden, dtype=x.dtype, device=x.device)
+    _C.check(lib.b200_moe_gather_rows(xs.data_ptr(), x.data_ptr(), plan.offsets.data_ptr(),
+                                      plan.sorted_pair.data_ptr(), pairs, n_local, k, hidden,
+                                      x.stride(0) if T > 1 else hidden, _dt(x), _stream()),
+             "b200_moe_gather_rows")
+    _C.check(lib.b200_moe_gemm_gate_up_umma(h.data_ptr(), xs.data_ptr(), w13.data_ptr(),
+                                            plan.offsets.data_ptr(), pairs, hidden, inter, n_local,
+                                            _dt(x), _stream()), "b200_moe_gemm_gate_up_umma")
+    _C.check(lib.b200_moe_gemm_down_umma(y.data_ptr(), h.data_ptr(), w2.data_ptr(), plan.offsets.data_ptr(),
+                                         plan.sorted_pair.data_ptr(), topk_weights.data_ptr(), pairs, inter,
+                                         hidden, n_local, _dt(x), _stream()), "b200_moe_gemm_down_umma")
+    return y
 
 
 def _moe_expert_gemms_library(x, w13, w2, topk_weights, plan: MoePlan) -> torch.Tensor:

@@ -204,23 +204,30 @@ def test_tiny_qwen3_moe_cuda_graph_equals_eager():
     assert outs[0] == outs[1]
 
 
-def test_library_grouped_gemm_path_matches_the_kernel_path(monkeypatch):
-    """B200_MOE_LIBRARY_GEMM_ROWS: prefill-sized batches through torch._grouped_mm (library GEMM)
-    around our gather / SiluAndMul / combine kernels must agree with the hand-written expert GEMMs."""
+@pytest.mark.parametrize("big", ["umma", "library"])
+def test_big_gemm_paths_match_the_streaming_kernels(monkeypatch, big):
+    """B200_MOE_BIG_GEMM: prefill-sized batches through the tcgen05 grouped GEMM (csrc/moe_umma.cu) or
+    through torch._grouped_mm must agree with the weight-streaming expert GEMMs -- full and
+    expert-parallel plans, row counts that are not multiples of the 128-row tile, an empty expert."""
     from nanovllm import ops
     g = torch.Generator().manual_seed(9)
     bf = torch.bfloat16
-    T, k, E, hidden, inter = 1500, 4, 8, 256, 128
-    x = torch.randn(T, hidden, generator=g).to(bf).cuda()
-    w13 = (hidden ** -0.5 * torch.randn(E, 2 * inter, hidden, generator=g)).to(bf).cuda()
-    w2 = (inter ** -0.5 * torch.randn(E, hidden, inter, generator=g)).to(bf).cuda()
-    ids = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(T)]).to(torch.int32).cuda()
-    w = torch.rand(T, k, generator=g)
-    w = (w / w.sum(-1, keepdim=True)).to(bf).cuda()
-    for begin, n in ((0, E), (4, 4)):
-        plan = ops.moe_align(ids, begin, n)
-        monkeypatch.setattr(ops, "_MOE_LIBRARY_GEMM_ROWS", 0)
-        a = ops.moe_experts(x, w13[begin:begin + n].contiguous(), w2[begin:begin + n].contiguous(), ids, w, plan)
-        monkeypatch.setattr(ops, "_MOE_LIBRARY_GEMM_ROWS", 64)
-        b = ops.moe_experts(x, w13[begin:begin + n].contiguous(), w2[begin:begin + n].contiguous(), ids, w, plan)
-        _close(b, a, f"library vs kernel, experts [{begin},{begin + n})")
+    for T, k, E, hidden, inter in ((1500, 4, 8, 256, 128), (333, 2, 4, 2048, 768), (700, 1, 3, 128, 64)):
+        x = torch.randn(T, hidden, generator=g).to(bf).cuda()
+        w13 = (hidden ** -0.5 * torch.randn(E, 2 * inter, hidden, generator=g)).to(bf).cuda()
+        w2 = (inter ** -0.5 * torch.randn(E, hidden, inter, generator=g)).to(bf).cuda()
+        ids = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(T)]).to(torch.int32)
+        if E == 3:
+            ids[ids == 1] = 2                           # expert 1 receives nothing
+        ids = ids.cuda()
+        w = torch.rand(T, k, generator=g)
+        w = (w / w.sum(-1, keepdim=True)).to(bf).cuda()
+        for begin, n in ((0, E), (E // 2, E - E // 2)):
+            plan = ops.moe_align(ids, begin, n)
+            wa, wb = w13[begin:begin + n].contiguous(), w2[begin:begin + n].contiguous()
+            monkeypatch.setattr(ops, "_MOE_BIG_GEMM", "")
+            a = ops.moe_experts(x, wa, wb, ids, w, plan)
+            monkeypatch.setattr(ops, "_MOE_BIG_GEMM", big)
+            monkeypatch.setattr(ops, "_MOE_BIG_GEMM_ROWS", 1)
+            b = ops.moe_experts(x, wa, wb, ids, w, plan)
+            _close(b, a, f"{big} vs streaming kernel, T={T} experts [{begin},{begin + n})")

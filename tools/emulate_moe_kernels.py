@@ -262,7 +262,39 @@ def check_combine_order():
     print("ok combine order")
 
 
+def check_umma_tile_walk():
+    """moe_umma_gemm_kernel: blockIdx.y -> (expert, 128-row tile) by walking the offsets; the grid's
+    upper bound (pairs/128 + experts) must cover every tile, every row must be stored exactly once,
+    and rows a tile computes past its expert's end must be discarded."""
+    rng = np.random.default_rng(3)
+    for trial in range(50):
+        E = int(rng.integers(1, 20))
+        counts = rng.integers(0, 400, E) * (rng.random(E) < 0.8)
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        pairs = int(offsets[-1] + rng.integers(0, 300))          # capacity >= local pairs
+        grid_y = (pairs + 127) // 128 + E
+        stored = np.zeros(pairs + 256, np.int64)
+        for tile in range(grid_y):
+            e, t = -1, 0
+            for i in range(E):
+                b, c = offsets[i], offsets[i + 1] - offsets[i]
+                nt = (c + 127) >> 7
+                if tile < t + nt:
+                    e, m0, row_begin, cnt = i, (tile - t) << 7, b, c
+                    break
+                t += nt
+            if e < 0:
+                continue
+            for row in range(128):
+                if m0 + row < cnt:
+                    stored[row_begin + m0 + row] += 1
+        assert (stored[:offsets[-1]] == 1).all() and (stored[offsets[-1]:] == 0).all(), trial
+        assert sum((c + 127) // 128 for c in counts) <= grid_y
+    print("ok umma tile walk")
+
+
 if __name__ == "__main__":
+    check_umma_tile_walk()
     check_align()
     check_gemm()
     check_combine_order()

@@ -23,6 +23,7 @@ if [ "${1:-}" = "tp" ]; then
 fi
 run moe_emulation       300 python tools/emulate_moe_kernels.py
 run moe_gpu             900 env B200_RUN_MOE=1 python -m pytest tests/test_z_moe_gpu.py -q
+run moe_30b_big_umma    900 env B200_MOE_BIG_GEMM=umma python bench.py --model qwen3-30b-a3b --no-cpu-baseline --steps 16 --warmup 4 --mem-util 0.85
 run umma2_kernels       600 env B200_PREFILL_KERNEL=umma2 python -m pytest tests/test_kernels_gpu.py -q -k prefill
 run umma2_engine        900 env B200_PREFILL_KERNEL=umma2 python -m pytest tests/test_engine_gpu.py -q -k "tiny_model or ragged or prefix_cache or llama"
 run chunked_prefill     600 env B200_RUN_STAGED=1 python -m pytest tests/test_z_staged_gpu.py -q -k chunked
