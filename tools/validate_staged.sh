@@ -28,6 +28,8 @@ run umma2_kernels       600 env B200_PREFILL_KERNEL=umma2 python -m pytest tests
 run umma2_engine        900 env B200_PREFILL_KERNEL=umma2 python -m pytest tests/test_engine_gpu.py -q -k "tiny_model or ragged or prefix_cache or llama"
 run chunked_prefill     600 env B200_RUN_STAGED=1 python -m pytest tests/test_z_staged_gpu.py -q -k chunked
 run kbench_vs_fa2       600 python tools/kbench.py all
+run ref_workload_b256    600 python tools/ref_bench_workload.py
+run ref_workload_b16     600 python tools/ref_bench_workload.py --block-size 16
 run bench_default       600 python bench.py --no-cpu-baseline --steps 64 --warmup 4
 run bench_umma2         600 env B200_PREFILL_KERNEL=umma2 python bench.py --no-cpu-baseline --steps 64 --warmup 4
 run bench_moe_30b       900 python bench.py --model qwen3-30b-a3b --no-cpu-baseline --steps 32 --warmup 4 --mem-util 0.85
