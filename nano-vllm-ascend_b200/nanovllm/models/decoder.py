@@ -14,6 +14,7 @@ o GEMM -> fused add+RMSNorm -> gate_up GEMM -> fused SiluAndMul -> down GEMM.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -28,6 +29,21 @@ from ..layers.linear import (MergedColumnParallelLinear, QKVParallelLinear, RowP
                              tp_rank_size)
 from ..layers.rotary_embedding import RotaryEmbedding, get_rope
 from ..utils.context import get_context
+
+
+# Experiment (off by default): while the HBM-streaming decode attention kernel runs, a side stream
+# prefetches the weights of the GEMMs that follow it into L2 (csrc/kv_scatter.cu, b200_l2_prefetch).
+# "1": evict-last policy, "2": default policy.
+_L2_PREFETCH = os.environ.get("B200_DECODE_L2_PREFETCH", "0")
+_L2_PREFETCH_CTAS = int(os.environ.get("B200_DECODE_L2_PREFETCH_CTAS", "16"))
+_side_streams: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    s = _side_streams.get(device)
+    if s is None:
+        s = _side_streams[device] = torch.cuda.Stream(device=device)
+    return s
 
 
 @dataclass
@@ -92,6 +108,24 @@ class DecoderAttention(nn.Module):
             self.k_norm = RMSNorm(self.head_dim, eps=spec.rms_eps)
         else:
             self.q_norm = self.k_norm = None
+        self.prefetch_next: list = []        # weights used right after this layer's attention (set by the model)
+        self._prefetch = None
+
+    def _attend(self, attn, q, k, v, ctx):
+        """Attention, optionally with the L2 prefetch of the following GEMMs' weights forked onto a
+        side stream for the duration of the (decode) attention kernel."""
+        if _L2_PREFETCH == "0" or ctx.is_prefill or not self.prefetch_next:
+            return attn(q, k, v, kv_stored=not attn.fp8_cache)
+        if self._prefetch is None:
+            self._prefetch = ops.L2Prefetch(self.prefetch_next, evict_last=_L2_PREFETCH == "1",
+                                            num_ctas=_L2_PREFETCH_CTAS)
+        main = torch.cuda.current_stream()
+        side = _side_stream(q.device)
+        side.wait_stream(main)               # fork (inside graph capture: a parallel branch)
+        self._prefetch.launch(side)
+        o = attn(q, k, v, kv_stored=not attn.fp8_cache)
+        main.wait_stream(side)               # join
+        return o
 
     def forward(self, positions: torch.Tensor, hidden_states: torch.Tensor) -> torch.Tensor:
         qkv = self.qkv_proj(hidden_states)
@@ -109,7 +143,7 @@ class DecoderAttention(nn.Module):
         q = qkv[:, :self.q_size].unflatten(1, (self.num_heads, self.head_dim))
         k = qkv[:, self.q_size:self.q_size + self.kv_size].unflatten(1, (self.num_kv_heads, self.head_dim))
         v = qkv[:, self.q_size + self.kv_size:].unflatten(1, (self.num_kv_heads, self.head_dim))
-        o = attn(q, k, v, kv_stored=not attn.fp8_cache)   # fp8 cache: attn runs the quantising scatter
+        o = self._attend(attn, q, k, v, ctx)              # fp8 cache: attn runs the quantising scatter
         return self.o_proj(o)
 
 
@@ -171,6 +205,15 @@ class DecoderModel(nn.Module):
                          RotaryEmbedding(spec.head_dim, spec.head_dim, spec.max_position, spec.rope_theta), i)
             for i in range(spec.num_layers)])
         self.norm = RMSNorm(spec.hidden_size, eps=spec.rms_eps)
+        for i, layer in enumerate(self.layers):       # consumed only when B200_DECODE_L2_PREFETCH is set
+            nxt = [layer.self_attn.o_proj.weight]
+            if isinstance(layer.mlp, DecoderMLP):
+                nxt += [layer.mlp.gate_up_proj.weight, layer.mlp.down_proj.weight]
+            else:
+                nxt.append(layer.mlp.gate.weight)
+            if i + 1 < len(self.layers):
+                nxt.append(self.layers[i + 1].self_attn.qkv_proj.weight)
+            layer.self_attn.prefetch_next = nxt
 
     def forward(self, input_ids, positions):
         hidden_states = self.embed_tokens(input_ids)

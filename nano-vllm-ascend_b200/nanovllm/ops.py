@@ -296,6 +296,26 @@ def sample(logits, temperatures=None, seed=0, step=0, out=None, step_offset=None
     return out
 
 
+# ------------------------------------------------------------------ L2 weight prefetch (experiment)
+class L2Prefetch:
+    """Prebuilt arguments of b200_l2_prefetch over a fixed set of (weight) tensors; `launch`
+    enqueues the prefetch kernel on the given stream. See csrc/kv_scatter.cu."""
+
+    def __init__(self, tensors, evict_last: bool = True, num_ctas: int = 16):
+        import ctypes
+        tensors = [t for t in tensors if t is not None and t.numel() > 0][:8]
+        _need_cuda(*tensors)
+        self._keep = tensors
+        self.n = len(tensors)
+        self.ptrs = (ctypes.c_void_p * max(self.n, 1))(*[t.data_ptr() for t in tensors])
+        self.sizes = (ctypes.c_int64 * max(self.n, 1))(*[t.numel() * t.element_size() for t in tensors])
+        self.evict_last, self.num_ctas = int(evict_last), int(num_ctas)
+
+    def launch(self, stream: torch.cuda.Stream) -> None:
+        _C.check(_C.load().b200_l2_prefetch(self.ptrs, self.sizes, self.n, self.evict_last, self.num_ctas,
+                                            stream.cuda_stream), "b200_l2_prefetch")
+
+
 # ------------------------------------------------------------------ sparse MoE (csrc/moe.cu)
 class MoePlan:
     """Device-side dispatch plan of one MoE layer call (b200_moe_align): fixed-capacity buffers,

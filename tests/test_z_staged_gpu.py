@@ -81,3 +81,10 @@ def test_nvls_allreduce_kernel_and_tp2_engine():
 def test_moe_kernels_and_engine():
     """csrc/moe.cu + layers/moe.py + models/qwen3_moe.py: tests/test_z_moe_gpu.py."""
     _pytest_child(["tests/test_z_moe_gpu.py"], {"B200_RUN_MOE": "1"}, 900)
+
+
+def test_decode_l2_weight_prefetch_keeps_results():
+    """B200_DECODE_L2_PREFETCH=1: the side-stream L2 prefetch next to decode attention (forked and
+    joined inside the captured graph) must not change a single token."""
+    _pytest_child(["tests/test_engine_gpu.py", "-k", "tiny_model or cuda_graph_decode_equals_eager"],
+                  {"B200_DECODE_L2_PREFETCH": "1"}, 600)

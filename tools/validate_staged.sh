@@ -31,6 +31,9 @@ run kbench_vs_fa2       600 python tools/kbench.py all
 run ref_workload_b256    600 python tools/ref_bench_workload.py
 run ref_workload_b16     600 python tools/ref_bench_workload.py --block-size 16
 run bench_default       600 python bench.py --no-cpu-baseline --steps 64 --warmup 4
+run l2prefetch_engine   600 env B200_DECODE_L2_PREFETCH=1 python -m pytest tests/test_engine_gpu.py -q -k "tiny_model or cuda_graph_decode_equals_eager"
+run bench_l2prefetch1   600 env B200_DECODE_L2_PREFETCH=1 python bench.py --no-cpu-baseline --steps 64 --warmup 4
+run bench_l2prefetch2   600 env B200_DECODE_L2_PREFETCH=2 python bench.py --no-cpu-baseline --steps 64 --warmup 4
 run bench_umma2         600 env B200_PREFILL_KERNEL=umma2 python bench.py --no-cpu-baseline --steps 64 --warmup 4
 run bench_moe_30b       900 python bench.py --model qwen3-30b-a3b --no-cpu-baseline --steps 32 --warmup 4 --mem-util 0.85
 run timeline_moe_30b    900 python tools/step_timeline.py --model qwen3-30b-a3b --mem-util 0.85 --out gpurun_out/timeline_moe_30b.txt
