@@ -13,12 +13,24 @@ number to put beside the reference's README table.
 import argparse
 import json
 import os
+import random
 import sys
 import time
-from random import randint, seed
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "nano-vllm-ascend_b200"))
+
+
+def workload(n_requests: int = 256, longest_prompt: int = 1024, longest_output: int = 1024):
+    """The request set of the reference's benchmark, drawn in its order from Random(0): every prompt's
+    length then its ids, and only afterwards every output budget (bench/bench.py:29-31)."""
+    rng = random.Random(0)
+    prompts = []
+    for _ in range(n_requests):
+        length = rng.randint(100, longest_prompt)
+        prompts.append([rng.randint(0, 10000) for _ in range(length)])
+    budgets = [rng.randint(100, longest_output) for _ in range(n_requests)]
+    return prompts, budgets
 
 
 def main():
@@ -31,21 +43,18 @@ def main():
     ap.add_argument("--kv-cache-dtype", default="auto")
     args = ap.parse_args()
     from nanovllm import LLM, SamplingParams
-    seed(0)
-    num_seqs, max_input_len, max_output_len = 256, 1024, 1024
+    prompts, budgets = workload()
     llm = LLM(args.model, enforce_eager=args.enforce_eager, max_model_len=4096,
               max_num_seqs=args.max_num_seqs, tensor_parallel_size=args.tensor_parallel_size,
               kvcache_block_size=args.block_size, kv_cache_dtype=args.kv_cache_dtype)
-    prompt_token_ids = [[randint(0, 10000) for _ in range(randint(100, max_input_len))] for _ in range(num_seqs)]
-    sampling_params = [SamplingParams(temperature=0.6, ignore_eos=True, max_tokens=randint(100, max_output_len))
-                       for _ in range(num_seqs)]
-    llm.generate([[1, 2, 3, 4]], SamplingParams(max_tokens=16), use_tqdm=False)     # warm-up (bench.py:34)
+    params = [SamplingParams(temperature=0.6, ignore_eos=True, max_tokens=n) for n in budgets]
+    llm.generate([[1, 2, 3, 4]], SamplingParams(max_tokens=16), use_tqdm=False)     # warm-up request
     import torch
     torch.cuda.synchronize()
-    t = time.time()
-    llm.generate(prompt_token_ids, sampling_params, use_tqdm=False)
-    t = time.time() - t
-    total_tokens = sum(sp.max_tokens for sp in sampling_params)
+    t0 = time.perf_counter()
+    llm.generate(prompts, params, use_tqdm=False)
+    t = time.perf_counter() - t0
+    total_tokens = sum(budgets)
     print(json.dumps({"workload": "reference bench/bench.py (256 seqs, in U(100,1024), out U(100,1024))",
                       "model": args.model, "kvcache_block_size": args.block_size,
                       "tensor_parallel_size": args.tensor_parallel_size, "enforce_eager": args.enforce_eager,
