@@ -138,15 +138,18 @@ prefill_umma2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_expect_tx(&full[s], KTILE);
           tma_load_3d(ring + s * KTILE, tm, &full[s], 0, k0 + n0, kvh * CH, pol_keep);
         } else {
+          // Every op of the tile is issued: boxes past the end of the sequence use an out-of-range
+          // row, which TMA zero-fills without touching memory -- P is exactly 0 there, but 0 x (stale
+          // shared memory that happens to hold an Inf/NaN pattern) would poison O.
           const int rb = p.kv_rows_box;
-          const int nops = min(k2BN / rb, (Lk - n0 + rb - 1) / rb);
+          const int nops = k2BN / rb;
           const int per_op = p.kv_split ? CH : 1;
           const int op_bytes = rb * 128 * (p.kv_split ? 1 : CH);
           mbar_expect_tx(&full[s], nops * per_op * op_bytes);
           for (int o = 0; o < nops; ++o) {
             const int tok = n0 + o * rb;
             const int entry = tok / p.block_size;
-            const int blk = p.block_tables[(int64_t)seq * p.bt_stride + entry];
+            const int blk = tok < Lk ? p.block_tables[(int64_t)seq * p.bt_stride + entry] : -1;
             const int row = blk < 0 ? -(1 << 30) : blk * p.block_size + (tok - entry * p.block_size);
             for (int c = 0; c < per_op; ++c) {
               const int dst = (p.kv_split ? c * KPANEL : 0) + o * rb * 128;
