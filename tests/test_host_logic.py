@@ -457,3 +457,22 @@ def test_moe_kernel_index_emulation():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emulate_moe_kernels.py")],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.count("ok ") >= 10, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_fused_allreduce_form_selection():
+    """comm.PeerAllReduce.mode(): which fused all-reduce form serves a message (pure host logic)."""
+    from nanovllm.comm import PeerAllReduce
+    c = object.__new__(PeerAllReduce)
+    c.world, c.max_bytes, c.two_shot, c.multicast_ptr, c.nvls_all = 8, 4 << 20, False, 0, False
+    assert c.mode(256, 1024, 2) == "one"            # Qwen3-0.6B TP=8: 7 x 512 KiB incoming
+    assert c.mode(256, 5120, 2) is None             # Qwen3-32B TP=8: 18 MB incoming -> NCCL by default
+    assert c.mode(4096, 5120, 2) is None            # prefill-sized: beyond the buffer
+    assert c.mode(256, 1030, 2) is None             # hidden % 8
+    c.two_shot = True
+    assert c.mode(256, 5120, 2) == "two" and c.mode(4, 5120 * 8, 2) is None
+    c.multicast_ptr = 0x7f0000000000                # NVLS region mapped
+    assert c.mode(256, 5120, 2) == "nvls"
+    assert c.mode(256, 1024, 2) == "one"            # small messages stay one-shot (one barrier)
+    assert c.mode(4, 8192, 2) == "one"              # fewer rows than ranks: never nvls
+    c.nvls_all = True
+    assert c.mode(256, 1024, 2) == "nvls" and c.mode(4, 8192, 2) == "one"
