@@ -21,7 +21,9 @@ run() {  # name, timeout seconds, command...
 }
 group_moe() {
   run moe_emulation       300 python tools/emulate_moe_kernels.py
+  run moe_diag_check      600 python tools/moe_diag.py check
   run moe_gpu             900 env B200_RUN_MOE=1 python -m pytest tests/test_z_moe_gpu.py -q
+  run moe_diag_bench      600 python tools/moe_diag.py bench
 }
 group_prefill() {
   run umma2_kernels       600 env B200_PREFILL_KERNEL=umma2 python -m pytest tests/test_kernels_gpu.py -q -k prefill
