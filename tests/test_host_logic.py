@@ -476,3 +476,57 @@ def test_fused_allreduce_form_selection():
     assert c.mode(4, 8192, 2) == "one"              # fewer rows than ranks: never nvls
     c.nvls_all = True
     assert c.mode(256, 1024, 2) == "nvls" and c.mode(4, 8192, 2) == "one"
+
+
+def _ep_worker(rank, world, port, out_q):
+    """Expert-parallel layout on a real process group (gloo): every rank builds its SparseMoeBlock
+    shard, fills it through the checkpoint-style weight loaders, evaluates ITS experts' partial sum with
+    the oracle on the shard's stacked weights, and the all-reduced result must equal the reference
+    block's golden output."""
+    import torch.distributed as dist
+    for p in (ROOT, os.path.join(ROOT, "nano-vllm-ascend_b200"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+    from nanovllm.layers.moe import SparseMoeBlock
+    from oracle import moe_ref
+    from test_oracle_golden import moe_block_weights
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "moe.pt"), weights_only=False)["e32_k4"]
+    E, k, hidden, inter = g["experts"], g["top_k"], g["hidden"], g["inter"]
+    gate, w13, w2 = moe_block_weights(E, hidden, inter, g["seed"])
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        blk = SparseMoeBlock(hidden, inter, E, k)            # rank / world come from the process group
+    finally:
+        torch.set_default_dtype(prev)
+    ok = (blk.ep_rank, blk.ep_size, blk.num_local, blk.expert_begin) == (rank, world, E // world, rank * E // world)
+    blk.gate.weight.weight_loader(blk.gate.weight, gate)
+    for name, ex in blk.experts.items():                      # checkpoint order: gate_proj, up_proj, down_proj
+        e = int(name)
+        ex.gate_up_proj.weight.weight_loader(ex.gate_up_proj.weight, w13[e, :inter], 0)
+        ex.gate_up_proj.weight.weight_loader(ex.gate_up_proj.weight, w13[e, inter:], 1)
+        ex.down_proj.weight.weight_loader(ex.down_proj.weight, w2[e])
+    local = range(blk.expert_begin, blk.expert_begin + blk.num_local)
+    full13 = [blk.w13[e - blk.expert_begin] if e in local else None for e in range(E)]
+    full2 = [blk.w2[e - blk.expert_begin] if e in local else None for e in range(E)]
+    part = moe_ref.sparse_moe_block(g["x"], blk.gate.weight.data, full13, full2, k, experts=set(local)).float()
+    dist.all_reduce(part)
+    err = (part - g["out"].float()).abs().max().item()
+    ok = ok and err <= 0.02 * g["out"].float().abs().max().item()
+    out_q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_expert_parallel_layout_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: True, 1: True}
