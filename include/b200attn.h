@@ -334,6 +334,19 @@ int b200_allreduce_add_rmsnorm_nvls(void* out, void* residual, const void* weigh
                                     void* const* peer_flags, void* state, int32_t world,
                                     int32_t rank, int32_t dtype, b200_stream_t stream);
 
+/* C1 (fused), NVLS with a row-sliced ("sequence-parallel") residual: rank r owns rows
+ * [r*ceil(rows/world), ...). For its rows it takes the in-switch sum of the partials, adds ITS
+ * residual rows, stores the new residual rows locally and multicasts the normalised rows into every
+ * rank's `out` region (`mc_out` = multicast address of a [rows, hidden] region of the symmetric
+ * allocation; read it afterwards through the local unicast address). One pass, two flag barriers, the
+ * residual never crosses a link. After the call `residual` is current ONLY in the caller's own row
+ * slice -- sufficient for a chain of such calls (each needs a residual row only on its owner), so all
+ * add+RMSNorm steps of one forward pass must use this form together. Flags/state as the other forms. */
+int b200_allreduce_add_rmsnorm_nvls_fused(void* residual, const void* weight, float eps, int32_t rows,
+                                          int32_t hidden, const void* mc_partial, void* mc_out,
+                                          void* const* peer_flags, void* state, int32_t world,
+                                          int32_t rank, int32_t dtype, b200_stream_t stream);
+
 /* Set-up helpers for the peer buffers (NOT hot path: they allocate / map memory, synchronously).
  * alloc: cudaMalloc + zero; get/open_handle: CUDA IPC (64-byte handle, peer access enabled
  * lazily); all return 0 or a cudaError_t value. */

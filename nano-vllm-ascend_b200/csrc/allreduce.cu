@@ -75,10 +75,15 @@ __device__ __forceinline__ void sum_parts(const uint4 (&part)[kMaxWorld], int wo
 // points of the reference (layers/layernorm.py:27-38): y materialised in T, add in fp32, norm in fp32.
 // load_sum(idx, acc) yields the 8 summed elements of 16-byte vector idx = row * hidden/8 + v.
 // blockDim.x * 4 vectors cover a row (hidden <= 8192). `red`: 32 floats of shared memory.
-template <typename T, typename LoadSum>
+struct PlainStore {
+  __device__ __forceinline__ void operator()(uint4* dst, const uint4& v) const { *dst = v; }
+};
+
+template <typename T, typename LoadSum, typename StoreOut = PlainStore>
 __device__ __forceinline__ void add_rmsnorm_row(int64_t row, int hidden, T* __restrict__ out,
                                                 T* __restrict__ residual, const T* __restrict__ weight,
-                                                float eps, float* red, LoadSum load_sum) {
+                                                float eps, float* red, LoadSum load_sum,
+                                                StoreOut store_out = StoreOut()) {
   const int nvec = hidden / 8;
   uint4* rrow = reinterpret_cast<uint4*>(residual + row * hidden);
   constexpr int kVec = 4;
@@ -137,7 +142,7 @@ __device__ __forceinline__ void add_rmsnorm_row(int64_t row, int hidden, T* __re
         const float b = to_f32<T>(from_f32<T>(__fmul_rn(vals[i][2 * j + 1], inv)));
         ow[j] = pack2<T>(__fmul_rn(a, wf.x), __fmul_rn(b, wf.y));
       }
-      orow[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      store_out(orow + v, make_uint4(ow[0], ow[1], ow[2], ow[3]));
     }
   }
 }
@@ -395,6 +400,85 @@ allreduce_add_rmsnorm_nvls_kernel(const ArMcParams q, T* __restrict__ out, T* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// NVLS, fully fused ("sequence-parallel residual"): rank r owns rows [r*slice, (r+1)*slice). For each
+// of them it pulls the in-switch sum of the partials, adds ITS copy of the residual row, writes the new
+// residual row LOCALLY and multicasts the normalised row into every rank's `out` region -- there is
+// no second pass over all rows and the residual never crosses a link: every later all-reduce of the
+// same forward pass needs a residual row only on the rank that owns it. Consequence for the caller:
+// after this call `residual` is current only in the caller's own row slice.
+struct McStore {
+  __device__ __forceinline__ void operator()(uint4* dst, const uint4& v) const { multimem_st(dst, v); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+allreduce_add_rmsnorm_nvls_fused_kernel(const ArMcParams q, T* __restrict__ residual,
+                                        const T* __restrict__ weight, float eps, int hidden) {
+  __shared__ float red[32];
+  __shared__ uint32_t s_ticket;
+  const ArParams& p = q.base;
+  pdl_wait();
+  const uint32_t epoch = p.state[0] + 1;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[2], 1u);
+  __syncthreads();
+  if (s_ticket == 0 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+
+  const int slice = (q.rows + p.world - 1) / p.world;
+  const int row0 = min(p.rank * slice, q.rows), row1 = min(row0 + slice, q.rows);
+  const uint4* mc_in = reinterpret_cast<const uint4*>(q.mc_partial);
+  T* mc_out = reinterpret_cast<T*>(q.mc_gather);          // multicast address of the `out` region
+  for (int row = row0 + blockIdx.x; row < row1; row += gridDim.x) {
+    add_rmsnorm_row<T>(row, hidden, mc_out, residual, weight, eps, red,
+                       [&](int64_t idx, float (&acc)[8]) {
+                         const uint4 y = multimem_ld_reduce_add<T>(mc_in + idx);
+                         const uint32_t w[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                         for (int j = 0; j < 4; ++j) {
+                           const float2 f = unpack2<T>(w[j]);
+                           acc[2 * j] = f.x;
+                           acc[2 * j + 1] = f.y;
+                         }
+                       },
+                       McStore());
+    __syncthreads();
+  }
+  // ---- every rank's rows have landed in my `out` region once all peers passed this barrier
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[3], 1u);
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + kMaxWorld + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + kMaxWorld + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(&p.state[1], 1u);
+    if (done == gridDim.x - 1) {
+      p.state[1] = 0;
+      p.state[2] = 0;
+      p.state[3] = 0;
+      __threadfence();
+      p.state[0] = epoch;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -524,6 +608,52 @@ extern "C" int b200_allreduce_add_rmsnorm_nvls(void* out, void* residual, const 
   else
     launch_pdl(allreduce_add_rmsnorm_nvls_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
                q, (__half*)out, (__half*)residual, (const __half*)weight, eps, hidden);
+  return finish_launch();
+}
+
+extern "C" int b200_allreduce_add_rmsnorm_nvls_fused(void* residual, const void* weight, float eps,
+                                                     int32_t rows, int32_t hidden, const void* mc_partial,
+                                                     void* mc_out, void* const* peer_flags, void* state,
+                                                     int32_t world, int32_t rank, int32_t dtype,
+                                                     b200_stream_t stream) {
+  B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
+  B200_RETURN_IF(rows < 0 || hidden <= 0 || world < 2 || world > kMaxWorld || rank < 0 || rank >= world,
+                 B200_ERR_BAD_SHAPE);
+  if (rows == 0) return B200_OK;
+  B200_RETURN_IF(!residual || !weight || !mc_partial || !mc_out || !peer_flags || !state,
+                 B200_ERR_NULL_POINTER);
+  B200_RETURN_IF(hidden % 8 != 0 || !aligned16(residual) || !aligned16(weight) || !aligned16(mc_partial) ||
+                     !aligned16(mc_out),
+                 B200_ERR_MISALIGNED);
+  B200_RETURN_IF(hidden > 8 * 256 * 4, B200_ERR_UNSUPPORTED);
+  ArMcParams q;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    q.base.bufs[r] = nullptr;
+    q.base.flags[r] = nullptr;
+  }
+  for (int r = 0; r < world; ++r) {
+    B200_RETURN_IF(!peer_flags[r], B200_ERR_NULL_POINTER);
+    q.base.flags[r] = reinterpret_cast<uint32_t*>(peer_flags[r]);
+  }
+  q.base.state = reinterpret_cast<uint32_t*>(state);
+  q.base.world = world;
+  q.base.rank = rank;
+  q.mc_partial = mc_partial;
+  q.mc_gather = mc_out;
+  q.local_gather = nullptr;
+  q.rows = rows;
+  // one CTA per owned row, co-resident (every CTA spins on peer flags). Ranks whose slice is empty
+  // still launch one CTA: it takes part in both barriers.
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int slice = (rows + world - 1) / world;
+  const int grid = slice < 1 ? 1 : (slice > sms ? sms : slice);
+  if (dtype == B200_DTYPE_BF16)
+    launch_pdl(allreduce_add_rmsnorm_nvls_fused_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0,
+               (cudaStream_t)stream, q, (__nv_bfloat16*)residual, (const __nv_bfloat16*)weight, eps, hidden);
+  else
+    launch_pdl(allreduce_add_rmsnorm_nvls_fused_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+               q, (__half*)residual, (const __half*)weight, eps, hidden);
   return finish_launch();
 }
 

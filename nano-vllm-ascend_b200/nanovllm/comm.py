@@ -58,7 +58,9 @@ class PeerAllReduce:
         # two-shot kernel: compiled and unit-tested on 2 GPUs only when enabled; opt-in until the
         # multi-GPU validation recorded in DESIGN.md section 6 is done
         self.two_shot = os.environ.get("B200_TWOSHOT_ALLREDUCE", "0") == "1"
-        self.nvls_all = nvls == "all"    # tuning aid: multicast form for every message size
+        self.nvls_all = nvls in ("all", "fused-all")   # tuning aid: multicast form for every message size
+        # "fused" / "fused-all": the one-pass form with a row-sliced residual (see allreduce.cu)
+        self.nvls_fused = nvls in ("fused", "fused-all")
         self._parity = 0
         self.pending = None          # (tensor, parity) written by the last deferred row-parallel GEMM
         dist.barrier()
@@ -112,7 +114,7 @@ class PeerAllReduce:
             return None
         if self.multicast_ptr and rows >= self.world and (
                 self.nvls_all or (self.world - 1) * nbytes > self.ONE_SHOT_MAX_INCOMING):
-            return "nvls"
+            return "nvls_fused" if self.nvls_fused else "nvls"
         if (self.world - 1) * nbytes <= self.ONE_SHOT_MAX_INCOMING:
             return "one"
         return "two" if self.two_shot and rows >= self.world else None
@@ -131,14 +133,26 @@ class PeerAllReduce:
 
     def allreduce_add_rmsnorm(self, out, residual, weight, eps, mode: str | None = None):
         """out <- RMSNorm(sum_r partial_r + residual) * weight; residual updated in place.
-        `out` may be any [rows, hidden] tensor (normally a fresh one; the partial buffer itself must
-        not be used: peers may still be reading it). `mode` forces "one"/"two" (tests); every rank
-        must pass the same value."""
+        `out` may be any [rows, hidden] tensor or None (a fresh one is made; the partial buffer itself
+        must not be used: peers may still be reading it). `mode` forces a form (tests); every rank
+        must pass the same value. In the "nvls_fused" form the result lives in the symmetric region
+        (returned view; `out` is ignored) and `residual` is current only in this rank's row slice."""
         view, parity = self.pending
         self.pending = None
         rows, hidden = view.shape
         from .ops import _dt, _stream
         mode = mode or self.mode(rows, hidden, view.dtype.itemsize)
+        if mode == "nvls_fused":
+            mc = self.multicast_ptr
+            n = rows * hidden * view.dtype.itemsize
+            _C.check(self.lib.b200_allreduce_add_rmsnorm_nvls_fused(
+                residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
+                mc + parity * self.max_bytes, mc + 2 * self.max_bytes, self._flags, self._state,
+                self.world, self.rank, _dt(view), _stream()), "b200_allreduce_add_rmsnorm_nvls_fused")
+            out = self.local[2 * self.max_bytes:2 * self.max_bytes + n].view(view.dtype).view(rows, hidden)
+            return out, residual
+        if out is None:
+            out = torch.empty_like(view)
         if mode == "nvls":
             mc = self.multicast_ptr
             _C.check(self.lib.b200_allreduce_add_rmsnorm_nvls(

@@ -463,7 +463,7 @@ def test_fused_allreduce_form_selection():
     """comm.PeerAllReduce.mode(): which fused all-reduce form serves a message (pure host logic)."""
     from nanovllm.comm import PeerAllReduce
     c = object.__new__(PeerAllReduce)
-    c.world, c.max_bytes, c.two_shot, c.multicast_ptr, c.nvls_all = 8, 4 << 20, False, 0, False
+    c.world, c.max_bytes, c.two_shot, c.multicast_ptr, c.nvls_all, c.nvls_fused = 8, 4 << 20, False, 0, False, False
     assert c.mode(256, 1024, 2) == "one"            # Qwen3-0.6B TP=8: 7 x 512 KiB incoming
     assert c.mode(256, 5120, 2) is None             # Qwen3-32B TP=8: 18 MB incoming -> NCCL by default
     assert c.mode(4096, 5120, 2) is None            # prefill-sized: beyond the buffer
@@ -476,6 +476,8 @@ def test_fused_allreduce_form_selection():
     assert c.mode(4, 8192, 2) == "one"              # fewer rows than ranks: never nvls
     c.nvls_all = True
     assert c.mode(256, 1024, 2) == "nvls" and c.mode(4, 8192, 2) == "one"
+    c.nvls_fused = True
+    assert c.mode(256, 5120, 2) == "nvls_fused" and c.mode(4, 8192, 2) == "one"
 
 
 def _ep_worker(rank, world, port, out_q):

@@ -47,6 +47,9 @@ _TWO_SHOT_CASES = [(256, 5120, "two"), (37, 5120, "two"), (1, 1024, "two"), (8, 
 # sequence; rows < world falls outside its contract (mode() never selects it there)
 _NVLS_CASES = [(256, 5120, "nvls"), (37, 5120, "nvls"), (8, 2048, "one"), (2, 1024, "nvls"),
                (256, 1024, "nvls"), (64, 2048, "two"), (255, 4096, "nvls"), (256, 8192, "nvls")]
+# the one-pass NVLS form with a row-sliced residual, alone and mixed with the other forms
+_NVLS_FUSED_CASES = [(256, 5120, "nvls_fused"), (37, 5120, "nvls_fused"), (2, 1024, "nvls_fused"),
+                     (8, 2048, "one"), (255, 4096, "nvls_fused"), (256, 1024, "nvls"), (3, 8192, "nvls_fused")]
 
 
 def _ar_worker(rank, world, port, out_q, cases):
@@ -75,10 +78,18 @@ def _ar_worker(rank, world, port, out_q, cases):
         buf.copy_(parts[rank].cuda())
         res_d = res.cuda()
         out = torch.empty(rows, hidden, dtype=torch.bfloat16, device="cuda")
-        comm.allreduce_add_rmsnorm(out, res_d, w.cuda(), 1e-6, mode=mode)
+        out, _ = comm.allreduce_add_rmsnorm(out, res_d, w.cuda(), 1e-6, mode=mode)
         torch.cuda.synchronize()
         d_out = (out.cpu().float() - want.float()).abs().max().item()
-        d_res = (res_d.cpu().float() - want_res.float()).abs().max().item()
+        got_res = res_d.cpu().float()
+        if mode == "nvls_fused":      # the residual is row-sliced: current only in this rank's rows
+            per = (rows + world - 1) // world
+            lo, hi = min(rank * per, rows), min((rank + 1) * per, rows)
+            untouched = torch.ones(rows, dtype=torch.bool)
+            untouched[lo:hi] = False
+            ok = ok and torch.equal(got_res[untouched], res.float()[untouched])
+            got_res, want_res = got_res[lo:hi], want_res[lo:hi]
+        d_res = (got_res - want_res.float()).abs().max().item() if got_res.numel() else 0.0
         # fp32 sum order differs from torch's stacked sum by <= 1 bf16 ulp of |x| ~ 4
         ok = ok and d_out < 0.07 and d_res < 0.07
     dist.barrier()
@@ -126,3 +137,4 @@ def test_fused_peer_allreduce_nvls_kernel():
     multicast mapping torch symmetric memory sets up)."""
     _need_gpus(2)
     assert _run_ar_workers(2, 28035, _NVLS_CASES) == {0: True, 1: True}
+    assert _run_ar_workers(2, 28037, _NVLS_FUSED_CASES) == {0: True, 1: True}

@@ -49,6 +49,7 @@ group_tp() {
   run tp_default        600 python -m pytest tests/test_tp_gpu.py -x -q
   run tp_nvls_kernel    300 env B200_NVLS_ALLREDUCE=1 python -m pytest tests/test_tp_gpu.py -q -k nvls
   run tp_nvls_engine    600 env B200_NVLS_ALLREDUCE=all python -m pytest tests/test_tp_gpu.py -q -k tp2_matches_tp1
+  run tp_nvls_fused_eng 600 env B200_NVLS_ALLREDUCE=fused-all python -m pytest tests/test_tp_gpu.py -q -k tp2_matches_tp1
   run tp_twoshot_engine 600 env B200_TWOSHOT_ALLREDUCE=1 python -m pytest tests/test_tp_gpu.py -q -k tp2_matches_tp1
 }
 case "${1:-default}" in
