@@ -273,7 +273,10 @@ int b200_moe_combine(void* out, const void* y, const int32_t* topk_ids, const in
  * 128-row x 128-weight-row tiles of one expert, TMA-staged SW128 panels, accumulators in TMEM.
  * b200_moe_gather_rows writes xs[pos, :hidden] = x[sorted_pair[pos] / top_k] for pos < offsets[num_local]
  * (TMA needs contiguous A rows); xs / h / y have `pairs` = tokens * top_k rows of capacity.
- * hidden % 64 == 0, inter % 64 == 0; down additionally hidden % 128 == 0. */
+ * hidden % 64 == 0, inter % 64 == 0; down additionally hidden % 128 == 0.
+ * Dense use: with num_local = 1 and offsets = {0, M} the two GEMMs are ordinary linear layers over M rows
+ * -- gate_up_umma = SiluAndMul(x . W_gate_up^T) in one kernel (layers/activation.py:11-13 fused into the
+ * GEMM of models/qwen3.py:115-117), down_umma with sorted_pair = topk_weights = NULL = x . W^T. */
 int b200_moe_gather_rows(void* xs, const void* x, const int32_t* offsets, const int32_t* sorted_pair,
                          int32_t pairs, int32_t num_local, int32_t top_k, int32_t hidden,
                          int64_t x_stride, int32_t dtype, b200_stream_t stream);

@@ -166,7 +166,12 @@ moe_umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     } else {
-      const float sc = valid ? to_f32<T>(reinterpret_cast<const T*>(p.pair_scale)[p.sorted_pair[pos]]) : 0.f;
+      // pair_scale == nullptr: a plain (dense) GEMM epilogue -- used when the kernel serves an ordinary
+      // linear layer as a one-expert group (ops.linear_umma)
+      const float sc = !valid ? 0.f
+                       : p.pair_scale == nullptr
+                           ? 1.f
+                           : to_f32<T>(reinterpret_cast<const T*>(p.pair_scale)[p.sorted_pair[pos]]);
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t a[32];
@@ -262,7 +267,7 @@ static int moe_umma_common(bool gate_up, void* out, const void* a, const void* w
   B200_RETURN_IF(K % 64 != 0 || n_out % (gate_up ? 64 : 128) != 0 || num_local > 256, B200_ERR_UNSUPPORTED);
   if (pairs == 0) return B200_OK;
   B200_RETURN_IF(!out || !a || !w || !offsets, B200_ERR_NULL_POINTER);
-  B200_RETURN_IF(!gate_up && (!sorted_pair || !pair_scale), B200_ERR_NULL_POINTER);
+  B200_RETURN_IF(!gate_up && ((sorted_pair == nullptr) != (pair_scale == nullptr)), B200_ERR_NULL_POINTER);
   B200_RETURN_IF(!aligned16(out) || !aligned16(a) || !aligned16(w), B200_ERR_MISALIGNED);
   CUtensorMap ma, mw;
   int rc = get_panel_map(a, pairs, (int64_t)K * 2, K / 64, 128, 1, dtype, &ma);

@@ -37,6 +37,9 @@ from ..utils.context import get_context
 _L2_PREFETCH = os.environ.get("B200_DECODE_L2_PREFETCH", "0")
 _L2_PREFETCH_CTAS = int(os.environ.get("B200_DECODE_L2_PREFETCH_CTAS", "16"))
 _side_streams: dict = {}
+# Experiment (off by default): decode-sized gate|up GEMM + SiluAndMul as ONE tcgen05 kernel
+# (ops.gate_up_silu_umma) instead of cuBLAS + silu_and_mul.
+_FUSED_GATE_UP = os.environ.get("B200_FUSED_GATE_UP", "0") == "1"
 
 
 def _side_stream(device) -> torch.cuda.Stream:
@@ -157,7 +160,11 @@ class DecoderMLP(nn.Module):
         self.act_fn = SiluAndMul()
 
     def forward(self, x):
-        return self.down_proj(self.act_fn(self.gate_up_proj(x)))
+        gu = self.gate_up_proj
+        if (_FUSED_GATE_UP and x.dim() == 2 and x.shape[0] <= 512 and gu.bias is None and x.is_contiguous()
+                and x.shape[1] % 64 == 0 and gu.weight.shape[0] % 128 == 0):
+            return self.down_proj(ops.gate_up_silu_umma(x, gu.weight))
+        return self.down_proj(self.act_fn(gu(x)))
 
 
 class DecoderLayer(nn.Module):

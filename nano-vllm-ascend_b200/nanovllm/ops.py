@@ -296,6 +296,53 @@ def sample(logits, temperatures=None, seed=0, step=0, out=None, step_offset=None
     return out
 
 
+# ------------------------------------------------------------------ dense layers on the grouped tcgen05 kernel
+_dense_offsets: dict = {}
+
+
+def _dense_plan(rows: int, device) -> torch.Tensor:
+    """offsets = {0, rows}: one group holding every row (csrc/moe_umma.cu serves an ordinary linear
+    layer as a one-expert group). Cached per (rows, device) so that graph capture never allocates it."""
+    key = (rows, device)
+    t = _dense_offsets.get(key)
+    if t is None:
+        t = _dense_offsets[key] = torch.tensor([0, rows], dtype=torch.int32, device=device)
+    return t
+
+
+def gate_up_silu_umma(x: torch.Tensor, w_gate_up: torch.Tensor) -> torch.Tensor:
+    """SiluAndMul(x @ w_gate_up.T) in ONE kernel (experiment, B200_FUSED_GATE_UP=1): the gate|up GEMM of
+    a dense MLP with the activation as its TMEM epilogue, instead of cuBLAS + silu_and_mul.
+    x [M, K] contiguous; w_gate_up [2*I, K] (gate rows, then up rows); K % 64 == 0, I % 64 == 0."""
+    _need_cuda(x, w_gate_up)
+    M, K = x.shape
+    inter = w_gate_up.shape[0] // 2
+    if not x.is_contiguous() or not w_gate_up.is_contiguous() or w_gate_up.shape[1] != K:
+        raise ValueError("gate_up_silu_umma takes contiguous x [M, K] and w [2*I, K]")
+    h = torch.empty(M, inter, dtype=x.dtype, device=x.device)
+    _C.check(_C.load().b200_moe_gemm_gate_up_umma(h.data_ptr(), x.data_ptr(), w_gate_up.data_ptr(),
+                                                  _dense_plan(M, x.device).data_ptr(), M, K, inter, 1,
+                                                  _dt(x), _stream()), "b200_moe_gemm_gate_up_umma (dense)")
+    return h
+
+
+def linear_umma(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x @ w.T on the same kernel (plain epilogue). x [M, K]; w [N, K]; K % 64 == 0, N % 128 == 0."""
+    _need_cuda(x, w)
+    M, K = x.shape
+    N = w.shape[0]
+    if not x.is_contiguous() or not w.is_contiguous() or w.shape[1] != K:
+        raise ValueError("linear_umma takes contiguous x [M, K] and w [N, K]")
+    if out is None:
+        out = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    elif out.shape != (M, N) or not out.is_contiguous() or out.dtype != x.dtype:
+        raise ValueError("out must be a contiguous [M, N] tensor of x's dtype")
+    _C.check(_C.load().b200_moe_gemm_down_umma(out.data_ptr(), x.data_ptr(), w.data_ptr(),
+                                               _dense_plan(M, x.device).data_ptr(), None, None, M, K, N, 1,
+                                               _dt(x), _stream()), "b200_moe_gemm_down_umma (dense)")
+    return out
+
+
 # ------------------------------------------------------------------ L2 weight prefetch (experiment)
 class L2Prefetch:
     """Prebuilt arguments of b200_l2_prefetch over a fixed set of (weight) tensors; `launch`

@@ -445,7 +445,7 @@ def test_moe_entry_points_reject_bad_arguments():
     # tcgen05 grouped GEMMs (moe_umma.cu)
     assert lib.b200_moe_gemm_gate_up_umma(one, one, one, one, 256, 100, 64, 4, 0, None) == -3       # K % 64
     assert lib.b200_moe_gemm_down_umma(one, one, one, one, one, one, 256, 64, 192, 4, 0, None) == -3  # hidden % 128
-    assert lib.b200_moe_gemm_down_umma(one, one, one, one, None, one, 256, 64, 128, 4, 0, None) == -1
+    assert lib.b200_moe_gemm_down_umma(one, one, one, one, None, one, 256, 64, 128, 4, 0, None) == -1   # scale without pairs
     assert lib.b200_moe_gemm_gate_up_umma(one, one, one, one, 0, 128, 64, 4, 0, None) == 0          # no pairs
     assert lib.b200_moe_gather_rows(one, one, one, one, 16, 4, 2, 100, 100, 0, None) == -4          # hidden % 8
 

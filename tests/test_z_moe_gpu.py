@@ -231,3 +231,17 @@ def test_big_gemm_paths_match_the_streaming_kernels(monkeypatch, big):
             monkeypatch.setattr(ops, "_MOE_BIG_GEMM_ROWS", 1)
             b = ops.moe_experts(x, wa, wb, ids, w, plan)
             _close(b, a, f"{big} vs streaming kernel, T={T} experts [{begin},{begin + n})")
+
+
+@pytest.mark.parametrize("M,K,inter", [(256, 1024, 3072), (7, 128, 64), (300, 5120, 3200), (128, 2048, 768)])
+def test_dense_layers_on_the_grouped_tcgen05_kernel(M, K, inter):
+    """ops.gate_up_silu_umma / ops.linear_umma: the grouped kernel as a one-expert group = an ordinary
+    (fused) linear layer; against cuBLAS + the validated silu_and_mul kernel."""
+    from nanovllm import ops
+    g = torch.Generator().manual_seed(M + K)
+    bf = torch.bfloat16
+    x = torch.randn(M, K, generator=g).to(bf).cuda()
+    w = (K ** -0.5 * torch.randn(2 * inter, K, generator=g)).to(bf).cuda()
+    _close(ops.gate_up_silu_umma(x, w), ops.silu_and_mul(torch.nn.functional.linear(x, w)), ("gate_up", M, K, inter))
+    if (2 * inter) % 128 == 0:
+        _close(ops.linear_umma(x, w), torch.nn.functional.linear(x, w), ("linear", M, K, inter))

@@ -36,6 +36,8 @@ group_bench() {
   run l2prefetch_engine   600 env B200_DECODE_L2_PREFETCH=1 python -m pytest tests/test_engine_gpu.py -q -k "tiny_model or cuda_graph_decode_equals_eager"
   run bench_l2prefetch1   600 env B200_DECODE_L2_PREFETCH=1 python bench.py --no-cpu-baseline --steps 64 --warmup 4
   run bench_l2prefetch2   600 env B200_DECODE_L2_PREFETCH=2 python bench.py --no-cpu-baseline --steps 64 --warmup 4
+  run fused_gate_up_eng   600 env B200_FUSED_GATE_UP=1 python -m pytest tests/test_engine_gpu.py -q -k "tiny_model or cuda_graph_decode_equals_eager"
+  run bench_fused_gate_up 600 env B200_FUSED_GATE_UP=1 python bench.py --no-cpu-baseline --steps 64 --warmup 4
   run bench_umma2         600 env B200_PREFILL_KERNEL=umma2 python bench.py --no-cpu-baseline --steps 64 --warmup 4
   run ref_workload_b256   600 python tools/ref_bench_workload.py
   run ref_workload_b16    600 python tools/ref_bench_workload.py --block-size 16
