@@ -13,9 +13,9 @@
 //   * gate_up's weight tile is 64 gate rows + the 64 matching up rows (two TMA boxes into one
 //     panel), so SiluAndMul is the TMEM->register epilogue: thread = row, columns [0,64) = gate,
 //     [64,128) = up; down's epilogue multiplies by the pair's routing weight;
-//   * warp 0 = TMA producer (3-stage ring of 16 KB A + 16 KB W per 64-wide K block), warp 1 = MMA
-//     issuer, warps 2-5 = epilogue (one TMEM lane quarter each); 97 KB smem + 128 TMEM columns
-//     -> two CTAs per SM, so one CTA's epilogue overlaps the other's main loop;
+//   * warp 0 = TMA producer (3- or 6-stage ring of 16 KB A + 16 KB W per 64-wide K block), warp 1 =
+//     MMA issuer, warps 2-5 = epilogue (one TMEM lane quarter each); with 3 stages 97 KB smem + 128
+//     TMEM columns -> two CTAs per SM, so one CTA's epilogue overlaps the other's main loop;
 //   * grid = (N tiles, upper bound on row tiles = pairs/128 + experts): every CTA finds its
 //     (expert, row tile) by walking the offsets; CTAs past the last tile exit at once. A row tile
 //     that runs past its expert's rows computes them against the wrong weights and discards them
@@ -32,14 +32,16 @@ struct MoeUmmaParams {
   int num_local, K, n_out;
 };
 
-constexpr int kMuStages = 3;
+// Ring depth: 3 stages (97 KB, two CTAs per SM) for tensor-bound grouped GEMMs, where the second CTA's
+// main loop hides the first one's epilogue; 6 stages (193 KB, one CTA per SM) when the grid is small
+// and every CTA is a latency-bound weight stream (the dense decode layers of ops.gate_up_silu_umma).
 constexpr int kMuPanel = 128 * 128;                 // one 128-row SW128 panel (A or W), bytes
 constexpr int kMuStageBytes = 2 * kMuPanel;
 constexpr int kMuThreads = 192;
-constexpr int kMuSmemBytes = 1024 + kMuStages * kMuStageBytes + 128;
+constexpr int mu_smem_bytes(int stages) { return 1024 + stages * kMuStageBytes + 128; }
 
-template <typename T, bool kGateUp>
-__global__ void __launch_bounds__(kMuThreads, 2)
+template <typename T, bool kGateUp, int kMuStages>
+__global__ void __launch_bounds__(kMuThreads, kMuStages <= 3 ? 2 : 1)
 moe_umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const MoeUmmaParams p) {
   extern __shared__ __align__(1024) uint8_t mu_smem_raw[];
@@ -217,20 +219,34 @@ moe_gather_rows_kernel(T* __restrict__ xs, const T* __restrict__ x, const int32_
   }
 }
 
+template <typename T, bool kGateUp, int kStages>
+static int moe_umma_launch_s(const CUtensorMap& ma, const CUtensorMap& mw, const MoeUmmaParams& p,
+                             dim3 grid, cudaStream_t stream) {
+  auto kern = moe_umma_gemm_kernel<T, kGateUp, kStages>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         mu_smem_bytes(kStages));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  launch_pdl(kern, grid, dim3(kMuThreads), (size_t)mu_smem_bytes(kStages), stream, ma, mw, p);
+  return finish_launch();
+}
+
 template <typename T>
 static int moe_umma_launch(bool gate_up, const CUtensorMap& ma, const CUtensorMap& mw,
                            const MoeUmmaParams& p, int pairs, cudaStream_t stream) {
-  auto kern = gate_up ? moe_umma_gemm_kernel<T, true> : moe_umma_gemm_kernel<T, false>;
-  static bool configured[2] = {false, false};
-  if (!configured[gate_up]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMuSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    configured[gate_up] = true;
-  }
   const int row_tiles = (pairs + 127) / 128 + p.num_local;      // upper bound; surplus CTAs exit at once
   const dim3 grid(p.n_out / (gate_up ? 64 : 128), row_tiles);
-  launch_pdl(kern, grid, dim3(kMuThreads), (size_t)kMuSmemBytes, stream, ma, mw, p);
-  return finish_launch();
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool deep = (long long)grid.x * ((pairs + 127) / 128) <= 2ll * sms;   // few live CTAs: latency-bound
+  if (gate_up)
+    return deep ? moe_umma_launch_s<T, true, 6>(ma, mw, p, grid, stream)
+                : moe_umma_launch_s<T, true, 3>(ma, mw, p, grid, stream);
+  return deep ? moe_umma_launch_s<T, false, 6>(ma, mw, p, grid, stream)
+              : moe_umma_launch_s<T, false, 3>(ma, mw, p, grid, stream);
 }
 
 }  // namespace b200
