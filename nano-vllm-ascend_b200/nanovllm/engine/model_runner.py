@@ -31,7 +31,7 @@ from ..utils.context import get_context, reset_context, set_context
 from ..utils.loader import device_init, load_model, seeded_init
 from .sequence import Sequence
 
-_SHM_NAME = "nano_vllm_b200"
+_SHM_PREFIX = "nano_vllm_b200"
 
 
 def _resolve_dtype(hf_config) -> torch.dtype:
@@ -113,18 +113,21 @@ class ModelRunner:
 
     # ------------------------------------------------------------------ TP control plane
     def _attach_shared_memory(self):
+        # one segment per engine: the rendezvous port is unique per concurrently running engine on a
+        # host, so two tensor-parallel engines never share a control channel
+        name = f"{_SHM_PREFIX}_{self.config.hccl_port}"
         if self.rank == 0:
             try:
-                self.shm = SharedMemory(name=_SHM_NAME, create=True, size=2 ** 20)
+                self.shm = SharedMemory(name=name, create=True, size=2 ** 20)
             except FileExistsError:                   # stale segment from a crashed run
-                stale = SharedMemory(name=_SHM_NAME)
+                stale = SharedMemory(name=name)
                 stale.close()
                 stale.unlink()
-                self.shm = SharedMemory(name=_SHM_NAME, create=True, size=2 ** 20)
+                self.shm = SharedMemory(name=name, create=True, size=2 ** 20)
             dist.barrier()
         else:
             dist.barrier()
-            self.shm = SharedMemory(name=_SHM_NAME)
+            self.shm = SharedMemory(name=name)
             self.loop()
 
     def loop(self):
