@@ -219,6 +219,18 @@ int b200_sample(int64_t* out_tokens, const void* logits, const float* temperatur
                 uint64_t step, const int64_t* step_offset, int32_t dtype,
                 b200_stream_t stream);
 
+/* f2, vocab-sharded (tensor parallelism). Replaces the logits gather to rank 0 (layers/embed_head.py:62-65)
+ * + the full-vocabulary sampling pass there: each rank scores its own vocabulary shard
+ * logits [rows, vocab_local] (global index = index_offset + local index; the Gumbel draw is keyed by
+ * the GLOBAL index, so the shards see exactly the unsharded scores) and writes one int64 key per row,
+ *   key = order_preserving_u32(best score) << 31 | (0x7fffffff - global index of the winner).
+ * A MAX all-reduce of the keys over the ranks (8 bytes per row) is the global arg-max with
+ * b200_sample's tie rule; token id = 0x7fffffff - (key & 0x7fffffff). Same seed/step/step_offset
+ * contract as b200_sample; every rank must pass the same values. */
+int b200_sample_shard(int64_t* out_keys, const void* logits, const float* temperatures, int32_t rows,
+                      int32_t vocab_local, int64_t logits_stride, int32_t index_offset, uint64_t seed,
+                      uint64_t step, const int64_t* step_offset, int32_t dtype, b200_stream_t stream);
+
 /* L2 weight prefetch (experiment; the Python side enables it with B200_DECODE_L2_PREFETCH=1):
  * cp.async.bulk.prefetch.L2 over up to 8 byte ranges (16-byte aligned; HOST arrays of device
  * pointers / sizes), optionally with an evict-last policy. Meant for a side stream running next

@@ -375,6 +375,82 @@ sample_kernel(int64_t* __restrict__ out, const T* __restrict__ logits,
   }
 }
 
+// Vocab-sharded form of sample_kernel for tensor parallelism (replaces the logits gather of
+// layers/embed_head.py:62-65 + a full-vocabulary pass on rank 0): every rank scores ITS shard of
+// the vocabulary -- the Gumbel draw is a pure function of (seed, step, row, GLOBAL index), so the
+// shards together see exactly the scores of the unsharded kernel -- and emits per row one int64 key
+//   key = order_preserving_u32(best score) << 31  |  (0x7fffffff - global index of the winner)
+// so that a MAX all-reduce over the ranks (8 bytes per row) yields the global arg-max with the same
+// tie rule (lowest index); b200_sample_shard's caller decodes id = 0x7fffffff - (key & 0x7fffffff).
+template <typename T>
+__global__ void __launch_bounds__(1024)
+sample_shard_kernel(int64_t* __restrict__ out_keys, const T* __restrict__ logits,
+                    const float* __restrict__ temperatures, int vocab, int64_t stride, int index_offset,
+                    uint64_t seed, uint64_t step, const int64_t* __restrict__ step_offset) {
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  pdl_wait();
+  const int row = blockIdx.x;
+  const T* lrow = logits + (int64_t)row * stride;
+  const float temp = temperatures == nullptr ? 0.f : temperatures[row];
+  const bool greedy = !(temp > 0.f);
+  const float inv_t = greedy ? 1.f : 1.f / temp;
+  if (step_offset != nullptr) step += (uint64_t)*step_offset;
+  const uint64_t key64 = splitmix64(seed ^ splitmix64(step * 0x100000001B3ull + row));
+  const uint32_t key = (uint32_t)key64 ^ (uint32_t)(key64 >> 32);
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  auto consider = [&](float v, int local) {
+    const int i = local + index_offset;                  // global vocabulary index
+    if (!greedy) {
+      const uint32_t r = mix32(key + (uint32_t)i * 0x9E3779B1u);
+      const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      v = fmaf(v, inv_t, -0.6931471806f * __log2f(-0.6931471806f * __log2f(u)));
+    }
+    if (v > best || (v == best && i < best_i)) best = v, best_i = i;
+  };
+  const bool vec_ok = (stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int nvec = vec_ok ? vocab / 8 : 0;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    const uint4 q = ld_nc_v4(reinterpret_cast<const uint4*>(lrow) + vi);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack2<T>(w[j]);
+      consider(f.x, vi * 8 + 2 * j);
+      consider(f.y, vi * 8 + 2 * j + 1);
+    }
+  }
+  for (int i = nvec * 8 + threadIdx.x; i < vocab; i += blockDim.x) consider(to_f32<T>(lrow[i]), i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) best = ov, best_i = oi;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_val[warp] = best, s_idx[warp] = best_i;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? s_val[lane] : -INFINITY;
+    best_i = lane < nw ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) best = ov, best_i = oi;
+    }
+    if (lane == 0) {
+      if (best == 0.f) best = 0.f;                        // -0.0 and +0.0 compare equal: one key for both
+      uint32_t b = __float_as_uint(best);
+      b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);    // order-preserving map float -> u32
+      if (best_i == 0x7fffffff) best_i = index_offset;    // empty / all -inf shard: a valid id, lowest key
+      out_keys[row] = ((int64_t)b << 31) | (int64_t)(0x7fffffff - best_i);
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -461,5 +537,26 @@ extern "C" int b200_sample(int64_t* out_tokens, const void* logits, const float*
   else
     launch_pdl(sample_kernel<__half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, out_tokens,
                (const __half*)logits, temperatures, vocab, logits_stride, seed, step, step_offset);
+  return finish_launch();
+}
+
+extern "C" int b200_sample_shard(int64_t* out_keys, const void* logits, const float* temperatures,
+                                 int32_t rows, int32_t vocab_local, int64_t logits_stride,
+                                 int32_t index_offset, uint64_t seed, uint64_t step,
+                                 const int64_t* step_offset, int32_t dtype, b200_stream_t stream) {
+  B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
+  B200_RETURN_IF(rows < 0 || vocab_local <= 0 || logits_stride < vocab_local || index_offset < 0 ||
+                     (int64_t)index_offset + vocab_local > 0x7fffffff,
+                 B200_ERR_BAD_SHAPE);
+  if (rows == 0) return B200_OK;
+  B200_RETURN_IF(!out_keys || !logits, B200_ERR_NULL_POINTER);
+  if (dtype == B200_DTYPE_BF16)
+    launch_pdl(sample_shard_kernel<__nv_bfloat16>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, out_keys,
+               (const __nv_bfloat16*)logits, temperatures, vocab_local, logits_stride, index_offset, seed,
+               step, step_offset);
+  else
+    launch_pdl(sample_shard_kernel<__half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, out_keys,
+               (const __half*)logits, temperatures, vocab_local, logits_stride, index_offset, seed, step,
+               step_offset);
   return finish_launch();
 }

@@ -101,6 +101,10 @@ class ModelRunner:
             self.comm = PeerAllReduce(self.device)
             set_comm(self.comm)
         self.sampler = Sampler(seed=config.seed)
+        # Opt-in until validated on hardware: sample on every rank over its own vocabulary shard and
+        # MAX-all-reduce 8 bytes per row, instead of gathering [B, vocab] logits on rank 0, sampling
+        # there and broadcasting the ids (reference: embed_head.py:62-65 + sampler.py on rank 0).
+        self.sharded_sampling = self.world_size > 1 and os.environ.get("B200_SHARDED_SAMPLING", "0") == "1"
 
         self._warmup_prefill()
         self._allocate_kv_cache()
@@ -291,6 +295,7 @@ class ModelRunner:
         self.d_out = torch.zeros(B, dtype=torch.int64, device=self.device)
         self.h_out = torch.zeros(B, dtype=torch.int64, pin_memory=True)
         self.d_rng = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.d_keys = torch.zeros(B, dtype=torch.int64, device=self.device)     # sharded sampling keys
         self.h2d_bytes = self.d2h_bytes = 0        # decode-step traffic counters (bench.py e2e)
         self.launches_per_graph: dict[int, int] = {}
 
@@ -348,12 +353,24 @@ class ModelRunner:
     def _decode_step(self, bs: int):
         """Forward + logits + sampling for `bs` rows of the static buffers (graph body)."""
         hidden = self.model(self.d_ids[:bs], self.d_pos[:bs])
+        if self.sharded_sampling:
+            self.d_rng.add_(1)
+            self._sample_sharded(hidden, self.d_temp[:bs], self.d_keys[:bs], self.d_out[:bs])
+            return
         logits = self.model.compute_logits(hidden)
         self.d_rng.add_(1)
         if self.rank == 0:
             self.sampler(logits, self.d_temp[:bs], out=self.d_out[:bs], step_offset=self.d_rng)
         if self.world_size > 1:
             dist.broadcast(self.d_out[:bs], 0)
+
+    def _sample_sharded(self, hidden, temps, keys, out):
+        head = self.model.lm_head
+        self.sampler.shard_keys(head.local_logits(hidden), temps, head.vocab_start_idx, out=keys,
+                                step_offset=self.d_rng)
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+        from .. import ops
+        ops.decode_sample_keys(keys, out=out)
 
     def _buckets(self) -> list[int]:
         top = self.config.max_num_seqs
@@ -386,9 +403,17 @@ class ModelRunner:
         n = len(seqs)
         if is_prefill:
             ids, pos = self.prepare_prefill(seqs)
-            logits = self.model.compute_logits(self.model(ids, pos))
             out = self.d_out[:n] if n <= self.d_out.numel() else torch.empty(
                 n, dtype=torch.int64, device=self.device)
+            if self.sharded_sampling:
+                hidden = self.model(ids, pos)
+                temps = torch.tensor([0.0 if s.greedy else s.temperature for s in seqs],
+                                     dtype=torch.float32, pin_memory=True).to(self.device, non_blocking=True)
+                self.d_rng.add_(1)
+                self._sample_sharded(hidden, temps, torch.empty_like(out), out)
+                reset_context()
+                return out.tolist()
+            logits = self.model.compute_logits(self.model(ids, pos))
             if self.rank == 0:
                 temps = torch.tensor([0.0 if s.greedy else s.temperature for s in seqs],
                                      dtype=torch.float32, pin_memory=True).to(self.device, non_blocking=True)

@@ -47,6 +47,14 @@ class ParallelLMHead(VocabParallelEmbedding):
             raise ValueError("lm_head bias is not part of the reference path")
         super().__init__(num_embeddings, embedding_dim)
 
+    def local_logits(self, x):
+        """This rank's vocabulary shard of the logits, no collective (the sharded sampling tail,
+        Sampler.shard_keys, consumes it where it is)."""
+        context = get_context()
+        if context.is_prefill:
+            x = x[(context.cu_seqlens_q[1:] - 1).long()].contiguous()
+        return F.linear(x, self.weight)
+
     def forward(self, x):
         context = get_context()
         if context.is_prefill:

@@ -31,3 +31,17 @@ class Sampler(nn.Module):
         self.step += 1
         return ops.sample(logits, None if greedy else temperatures, seed=self.seed, step=self.step,
                           out=out, step_offset=step_offset)
+
+    def shard_keys(self, logits: torch.Tensor, temperatures: torch.Tensor | None, index_offset: int,
+                   greedy: bool = False, out: torch.Tensor | None = None,
+                   step_offset: torch.Tensor | None = None):
+        """Tensor parallelism without a logits gather: this rank's vocabulary shard -> one packed
+        (score, global index) key per row; the caller MAX-all-reduces the keys over the ranks and
+        decodes them with ``ops.decode_sample_keys``. Every rank must call this in lock step (the
+        step counter is part of the random stream)."""
+        real_bs = logits.shape[0] if temperatures is None else temperatures.shape[0]
+        if logits.shape[0] != real_bs:
+            logits = logits[:real_bs]
+        self.step += 1
+        return ops.sample_shard(logits, None if greedy else temperatures, seed=self.seed, step=self.step,
+                                index_offset=index_offset, out=out, step_offset=step_offset)

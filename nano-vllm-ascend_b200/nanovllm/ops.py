@@ -296,6 +296,34 @@ def sample(logits, temperatures=None, seed=0, step=0, out=None, step_offset=None
     return out
 
 
+def sample_shard(logits, temperatures=None, seed=0, step=0, index_offset=0, out=None, step_offset=None):
+    """Vocab-sharded sampling (tensor parallelism): packed (score, global index) keys of this rank's
+    shard, to be MAX-all-reduced over the ranks; see include/b200attn.h::b200_sample_shard."""
+    _need_cuda(logits, temperatures, step_offset)
+    rows, vocab = logits.shape
+    if logits.stride(1) != 1:
+        raise ValueError("logits must have unit inner stride")
+    if temperatures is not None and (temperatures.dtype != torch.float32 or
+                                     not temperatures.is_contiguous()):
+        raise TypeError("temperatures must be contiguous fp32")
+    if out is None:
+        out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    _C.check(_C.load().b200_sample_shard(out.data_ptr(), logits.data_ptr(), _ptr(temperatures), rows, vocab,
+                                         logits.stride(0) if rows > 1 else vocab, int(index_offset),
+                                         int(seed), int(step), _ptr(step_offset), _dt(logits), _stream()),
+             "b200_sample_shard")
+    return out
+
+
+def decode_sample_keys(keys: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Token ids from (all-reduced) sample_shard keys: id = 0x7fffffff - (key & 0x7fffffff)."""
+    ids = 0x7FFFFFFF - (keys & 0x7FFFFFFF)
+    if out is None:
+        return ids
+    out.copy_(ids)
+    return out
+
+
 # ------------------------------------------------------------------ dense layers on the grouped tcgen05 kernel
 _dense_offsets: dict = {}
 

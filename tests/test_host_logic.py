@@ -442,6 +442,8 @@ def test_moe_entry_points_reject_bad_arguments():
     assert lib.b200_moe_gemm_down(one, one, one, one, one, None, 64, 128, 4, 2, 0, None) == -1
     assert lib.b200_moe_combine(one, one, one, one, 4, 2, 100, 100, 0, None) == -4                 # hidden % 8
     assert lib.b200_moe_combine(one, one, one, one, 0, 2, 128, 128, 0, None) == 0                  # empty batch
+    assert lib.b200_sample_shard(one, one, None, 4, 1000, 1000, 2 ** 31 - 500, 0, 0, None, 0, None) == -2   # index overflow
+    assert lib.b200_sample_shard(None, one, None, 4, 1000, 1000, 0, 0, 0, None, 0, None) == -1
     # tcgen05 grouped GEMMs (moe_umma.cu)
     assert lib.b200_moe_gemm_gate_up_umma(one, one, one, one, 256, 100, 64, 4, 0, None) == -3       # K % 64
     assert lib.b200_moe_gemm_down_umma(one, one, one, one, one, one, 256, 64, 192, 4, 0, None) == -3  # hidden % 128
@@ -532,3 +534,27 @@ def test_expert_parallel_layout_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert results == {0: True, 1: True}
+
+
+def test_sharded_sampling_key_packing_arithmetic():
+    """The int64 key of b200_sample_shard, restated in numpy: MAX over keys == (max score, lowest
+    index) and the id decodes back, for negative / zero / infinite scores and exact ties."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+
+    def key(score: np.float32, idx: int) -> int:
+        score = np.float32(0.0) if score == 0.0 else score           # the kernel folds -0.0 into +0.0
+        b = int(np.float32(score).view(np.uint32))
+        b = (~b & 0xFFFFFFFF) if b & 0x80000000 else (b | 0x80000000)
+        return (b << 31) | (0x7FFFFFFF - idx)
+
+    for _ in range(200):
+        n = int(rng.integers(2, 50))
+        scores = rng.choice(np.array([-np.inf, -3.5, -0.0, 0.0, 1e-30, 2.25, 2.25, 7.0, np.inf], np.float32), n)
+        idx = rng.permutation(2 ** 20)[:n]
+        keys = [key(s, int(i)) for s, i in zip(scores, idx)]
+        assert all(0 <= k < 2 ** 63 for k in keys)
+        best = max(keys)
+        top = scores.max()
+        want = min(int(i) for s, i in zip(scores, idx) if s == top)      # float compare: -0.0 == 0.0
+        assert 0x7FFFFFFF - (best & 0x7FFFFFFF) == want

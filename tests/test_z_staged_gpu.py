@@ -88,3 +88,40 @@ def test_decode_l2_weight_prefetch_keeps_results():
     joined inside the captured graph) must not change a single token."""
     _pytest_child(["tests/test_engine_gpu.py", "-k", "tiny_model or cuda_graph_decode_equals_eager"],
                   {"B200_DECODE_L2_PREFETCH": "1"}, 600)
+
+
+def test_sharded_sampling_equals_full_vocabulary_sampling():
+    """b200_sample_shard on 1..8 vocabulary shards + a MAX over the keys == b200_sample on the whole
+    row, bit for bit: greedy rows, temperature rows (the Gumbel draw is keyed by the GLOBAL index),
+    ties (lowest index wins), a shard that is entirely -inf. Single GPU: the all-reduce is a torch max."""
+    import torch
+    from nanovllm import ops
+    g = torch.Generator().manual_seed(3)
+    rows, vocab = 37, 151936
+    logits = (3 * torch.randn(rows, vocab, generator=g)).to(torch.bfloat16).cuda()
+    logits[5, 1000:1010] = 30.0                      # a 10-way tie for the maximum inside one shard
+    logits[6, 10] = logits[6, vocab - 7] = 31.0      # a tie across the first and the last shard
+    logits[7, : vocab // 2] = float("-inf")          # an all -inf shard (world = 2)
+    temps = torch.rand(rows, generator=g) * 1.5
+    temps[::3] = 0.0                                 # every third row greedy
+    temps = temps.cuda()
+    off = torch.tensor([11], dtype=torch.int64, device="cuda")
+    for world in (1, 2, 4, 8):
+        per = vocab // world
+        for t in (None, temps):
+            want = ops.sample(logits, t, seed=5, step=9, step_offset=off)
+            keys = None
+            for r in range(world):
+                shard = logits[:, r * per:(r + 1) * per].contiguous()
+                k = ops.sample_shard(shard, t, seed=5, step=9, index_offset=r * per, step_offset=off)
+                keys = k if keys is None else torch.maximum(keys, k)
+            got = ops.decode_sample_keys(keys)
+            assert torch.equal(got, want), (world, t is None, (got != want).nonzero().flatten().tolist())
+    assert int(want[5]) >= 0 and int(ops.sample(logits, None)[5]) == 1000 and int(ops.sample(logits, None)[6]) == 10
+
+
+def test_sharded_sampling_tp2_engine_matches_tp1():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _pytest_child(["tests/test_tp_gpu.py", "-k", "tp2_matches_tp1"], {"B200_SHARDED_SAMPLING": "1"}, 600)

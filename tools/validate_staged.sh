@@ -28,6 +28,7 @@ group_moe() {
 group_prefill() {
   run umma2_kernels       600 env B200_PREFILL_KERNEL=umma2 python -m pytest tests/test_kernels_gpu.py -q -k prefill
   run umma2_engine        900 env B200_PREFILL_KERNEL=umma2 python -m pytest tests/test_engine_gpu.py -q -k "tiny_model or ragged or prefix_cache or llama"
+  run sharded_sampling    300 env B200_RUN_STAGED=1 python -m pytest tests/test_z_staged_gpu.py -q -k sharded_sampling_equals
   run chunked_prefill     600 env B200_RUN_STAGED=1 python -m pytest tests/test_z_staged_gpu.py -q -k chunked
 }
 group_bench() {
@@ -52,6 +53,7 @@ group_tp() {
   run tp_nvls_kernel    300 env B200_NVLS_ALLREDUCE=1 python -m pytest tests/test_tp_gpu.py -q -k nvls
   run tp_nvls_engine    600 env B200_NVLS_ALLREDUCE=all python -m pytest tests/test_tp_gpu.py -q -k tp2_matches_tp1
   run tp_nvls_fused_eng 600 env B200_NVLS_ALLREDUCE=fused-all python -m pytest tests/test_tp_gpu.py -q -k tp2_matches_tp1
+  run tp_sharded_sample 600 env B200_SHARDED_SAMPLING=1 python -m pytest tests/test_tp_gpu.py -q -k tp2_matches_tp1
   run tp_twoshot_engine 600 env B200_TWOSHOT_ALLREDUCE=1 python -m pytest tests/test_tp_gpu.py -q -k tp2_matches_tp1
 }
 case "${1:-default}" in

@@ -20,6 +20,7 @@ run tp${N}_32b_default   420 $TR --master-port 29602 $B
 run tp${N}_32b_twoshot   420 env B200_TWOSHOT_ALLREDUCE=1 $TR --master-port 29603 $B
 run tp${N}_32b_nvls      420 env B200_NVLS_ALLREDUCE=1 $TR --master-port 29604 $B
 run tp${N}_32b_nvlsfused 420 env B200_NVLS_ALLREDUCE=fused $TR --master-port 29607 $B
+run tp${N}_32b_nvls_shs  420 env B200_NVLS_ALLREDUCE=1 B200_SHARDED_SAMPLING=1 $TR --master-port 29608 $B
 run tp${N}_32b_nvls_tl   420 env B200_NVLS_ALLREDUCE=1 $TR --master-port 29605 tools/step_timeline.py --model qwen3-32b --tp --mem-util 0.85 --out gpurun_out/timeline_tp${N}_32b_nvls.txt
 run tp${N}_moe_30b       420 $TR --master-port 29606 bench.py --gpus $N --tp --model qwen3-30b-a3b --no-cpu-baseline --steps 32 --warmup 4 --mem-util 0.85
 cat gpurun_out/validate_tp_summary.log
