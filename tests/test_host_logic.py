@@ -551,7 +551,7 @@ def test_sharded_sampling_key_packing_arithmetic():
     for _ in range(200):
         n = int(rng.integers(2, 50))
         scores = rng.choice(np.array([-np.inf, -3.5, -0.0, 0.0, 1e-30, 2.25, 2.25, 7.0, np.inf], np.float32), n)
-        idx = rng.permutation(2 ** 20)[:n]
+        idx = rng.choice(2 ** 20, size=n, replace=False, shuffle=False)
         keys = [key(s, int(i)) for s, i in zip(scores, idx)]
         assert all(0 <= k < 2 ** 63 for k in keys)
         best = max(keys)
