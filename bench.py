@@ -41,6 +41,44 @@ METRIC = "decode_tokens_per_s"
 UNIT = "tokens/s"
 
 
+def moe_expert_roofline(runner, B, peak_gbs):
+    """Sparse-MoE models: the expert GEMMs (csrc/moe.cu) are the other HBM stream of a decode step.
+    Timed alone with CUDA events over every layer's own expert weights (>= 1 GB per layer, cold in L2);
+    algorithmic bytes per layer = experts hit x 3 x hidden x moe_intermediate x 2 B."""
+    from nanovllm import ops
+    from nanovllm.layers.moe import SparseMoeBlock
+    blocks = [m for m in runner.model.modules() if isinstance(m, SparseMoeBlock)]
+    blk = blocks[0]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, blk.hidden_size, device="cuda", generator=g).to(runner.dtype)
+    scores = torch.rand(B, blk.num_experts, device="cuda", generator=g)
+    ids = scores.topk(blk.top_k, dim=1).indices.to(torch.int32).contiguous()
+    w = torch.full((B, blk.top_k), 1.0 / blk.top_k, device="cuda").to(runner.dtype)
+    plan = ops.moe_align(ids, blk.expert_begin, blk.num_local)
+    hit = int((plan.offsets[1:] > plan.offsets[:-1]).sum())
+
+    def one_pass():
+        for b in blocks:
+            ops.moe_experts(x, b.w13, b.w2, ids, w, plan)
+    for _ in range(2):
+        one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    e0.record()
+    for _ in range(reps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    per_layer_s = e0.elapsed_time(e1) / 1e3 / (reps * len(blocks))
+    nbytes = hit * 3 * blk.hidden_size * blk.inter * x.element_size()
+    achieved = nbytes / per_layer_s / 1e9
+    return {"bound": "hbm", "kernel": "moe_gemm_kernel<gate_up> + <down> + moe_combine_kernel",
+            "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "algorithmic_bytes_per_launch": nbytes, "us_per_layer": per_layer_s * 1e6,
+            "experts_hit": hit, "local_experts": blk.num_local, "layers": len(blocks)}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +376,8 @@ def main():
                      "step_frac_of_kv_roofline": (B * K / dev_s) / (B / (step_kv_bytes / (peak * 1e9)))},
         "clocks": clk,
     }
+    if getattr(spec, "num_experts", 0):
+        line["moe_roofline"] = moe_expert_roofline(runner, B, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "qwen3-0.6b":
         tps, sec = cpu_reference_step(args.cpu_sample_seqs, ctx, args.block_size, 3, 1)
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
