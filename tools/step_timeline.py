@@ -74,14 +74,19 @@ def main():
     if rank == 0:
         agg = collections.OrderedDict()
         busy = 0.0
-        for ev in prof.events():
-            if ev.device_type != torch.autograd.DeviceType.CUDA:
-                continue
-            us = ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
-            name = ev.name[:110]
-            n, tot = agg.get(name, (0, 0.0))
-            agg[name] = (n + 1, tot + us)
-            busy += us
+        try:
+            for ev in prof.events():
+                if ev.device_type != torch.autograd.DeviceType.CUDA:
+                    continue
+                us = ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+                name = ev.name[:110]
+                n, tot = agg.get(name, (0, 0.0))
+                agg[name] = (n + 1, tot + us)
+                busy += us
+        except Exception as e:            # profiler event API drift: fall back to torch's own table
+            print(f"event walk failed ({type(e).__name__}: {e}); key_averages() instead")
+            print(prof.key_averages().table(row_limit=40))
+            agg, busy = collections.OrderedDict(), 1.0
         lines = [f"model={args.model} tp={world if args.tp else 1} batch={args.batch} ctx~{args.ctx} "
                  f"step (no profiler) = {plain_ms:.3f} ms; GPU-busy under profiler = "
                  f"{busy / args.steps / 1e3:.3f} ms/step over {args.steps} steps",
