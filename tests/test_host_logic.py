@@ -558,3 +558,9 @@ def test_sharded_sampling_key_packing_arithmetic():
         top = scores.max()
         want = min(int(i) for s, i in zip(scores, idx) if s == top)      # float compare: -0.0 == 0.0
         assert 0x7FFFFFFF - (best & 0x7FFFFFFF) == want
+    # the product's decoder of all-reduced keys (pure tensor arithmetic, device-agnostic)
+    from nanovllm import ops
+    ks = torch.tensor([key(np.float32(1.5), 7), key(np.float32(-2.0), 151935), key(np.float32(0.0), 0)])
+    assert ops.decode_sample_keys(ks).tolist() == [7, 151935, 0]
+    out = torch.zeros(3, dtype=torch.int64)
+    assert ops.decode_sample_keys(ks, out=out) is out and out.tolist() == [7, 151935, 0]
