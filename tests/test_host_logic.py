@@ -28,6 +28,31 @@ def test_library_exports_every_declared_symbol():
     assert lib.b200_launch_count() == 0
 
 
+def test_ctypes_prototypes_match_the_header_signatures():
+    """Argument count and argument class (pointer / int32 / int64 / uint64 / size_t / float) of every
+    ctypes prototype against the C declaration: a mismatch would not fail to load, it would pass
+    garbage to a kernel launch."""
+    from nanovllm import _C
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "b200attn.h")).read(), flags=re.S)
+    decls = re.findall(r"\b(?:int|int64_t|size_t|void|const char\*)\s+\**(b200_\w+)\s*\(([^;]*?)\)\s*;",
+                       header, flags=re.S)
+    assert len(decls) >= 30
+    scalar = {"float": ctypes.c_float, "int32_t": ctypes.c_int32, "int": ctypes.c_int32,
+              "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "size_t": ctypes.c_size_t}
+
+    def ctype_of(arg: str):
+        if "*" in arg or "b200_stream_t" in arg:
+            return ctypes.c_void_p
+        return scalar[arg.replace("const", "").split()[0]]
+    for name, args in decls:
+        args = args.strip()
+        want = [] if args in ("", "void") else [ctype_of(a.strip()) for a in args.split(",")]
+        got = list(_C.PROTOTYPES[name][1])
+        assert len(want) == len(got), (name, len(want), len(got))
+        for i, (w, g) in enumerate(zip(want, got)):
+            assert w is g or (w is ctypes.c_void_p and g is ctypes.c_char_p), (name, i, w, g)
+
+
 def test_bad_arguments_are_rejected_without_a_gpu():
     """Argument validation happens before any CUDA call, so it can be exercised on CPU."""
     from nanovllm import _C
