@@ -262,6 +262,51 @@ def check_combine_order():
     print("ok combine order")
 
 
+def check_route():
+    """moe_route_kernel, lane by lane: expert e lives in lane e % 32, slot e // 32; k rounds of
+    (per-lane best over slots, ties to the lower slot) -> (warp arg-max, ties to the lower index) ->
+    the owning lane retires the winner. Against a stable descending sort of the same probabilities."""
+    rng = np.random.default_rng(4)
+    for E, k in ((8, 2), (5, 2), (33, 1), (48, 6), (128, 8), (256, 8)):
+        VPL = (E + 31) // 32
+        VPL = 1 if VPL <= 1 else 2 if VPL <= 2 else 4 if VPL <= 4 else 8
+        for trial in range(40):
+            # coarse values -> many exact ties
+            logits = rng.integers(-3, 4, E).astype(np.float32) / 2
+            pe = np.exp(logits - logits.max())
+            probs = (pe / pe.sum()).astype(np.float32)
+            p = np.full((32, VPL), -1.0, np.float32)
+            for lane in range(32):
+                for i in range(VPL):
+                    e = lane + 32 * i
+                    if e < E:
+                        p[lane, i] = probs[e]
+            sel = []
+            for j in range(k):
+                bv = np.full(32, -1.0, np.float32)
+                bi = np.full(32, 0x7FFFFFFF, np.int64)
+                for lane in range(32):
+                    for i in range(VPL):
+                        if p[lane, i] > bv[lane]:
+                            bv[lane], bi[lane] = p[lane, i], lane + 32 * i
+                o = 16
+                while o > 0:                                   # butterfly arg-max
+                    nv, ni = bv.copy(), bi.copy()
+                    for lane in range(32):
+                        ov, oi = bv[lane ^ o], bi[lane ^ o]
+                        if ov > bv[lane] or (ov == bv[lane] and oi < bi[lane]):
+                            nv[lane], ni[lane] = ov, oi
+                    bv, bi = nv, ni
+                    o >>= 1
+                assert (bi == bi[0]).all()
+                w = int(bi[0])
+                p[w & 31, w >> 5] = -1.0
+                sel.append(w)
+            want = sorted(range(E), key=lambda e: (-probs[e], e))[:k]
+            assert sel == want, (E, k, sel, want)
+    print("ok route selection (ties -> lower index)")
+
+
 def check_umma_tile_walk():
     """moe_umma_gemm_kernel: blockIdx.y -> (expert, 128-row tile) by walking the offsets; the grid's
     upper bound (pairs/128 + experts) must cover every tile, every row must be stored exactly once,
@@ -294,6 +339,7 @@ def check_umma_tile_walk():
 
 
 if __name__ == "__main__":
+    check_route()
     check_umma_tile_walk()
     check_align()
     check_gemm()
