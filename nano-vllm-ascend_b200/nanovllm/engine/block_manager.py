@@ -85,6 +85,10 @@ class BlockManager:
 
     def allocate(self, seq: Sequence) -> None:
         assert not seq.block_table
+        # a re-admitted (preempted) sequence starts from scratch: the reference never resets this
+        # counter (block_manager.py:62-88) and ignores it in its runner; here prepare_prefill and the
+        # chunked scheduler consume it, so a stale value would skip tokens whose K/V are gone
+        seq.num_cached_tokens = 0
         hashes = self._chain(seq)
         # length of the cached prefix: leading blocks whose hash is known AND whose stored
         # tokens really are these tokens (hash collisions do not count as hits)

@@ -88,6 +88,16 @@ class LLMEngine:
 
     def step(self):
         seqs, is_prefill = self.scheduler.schedule()
+        if not seqs:
+            # nothing runnable: either idle, or the head of the queue can never be admitted (the
+            # reference spins forever here, scheduler.py:41-77 returning an empty batch each step)
+            if self.scheduler.waiting and not self.scheduler.running:
+                seq = self.scheduler.waiting[0]
+                raise RuntimeError(
+                    f"sequence of {len(seq)} tokens needs {seq.num_blocks} KV blocks but the pool "
+                    f"has {len(self.scheduler.block_manager.blocks)}: raise gpu_memory_utilization / "
+                    f"num_kvcache_blocks or lower max_model_len")
+            return [], 0
         token_ids = self.model_runner.call("run", seqs, is_prefill)
         num_tokens = -len(seqs)
         if is_prefill:

@@ -120,14 +120,18 @@ class ModelRunner:
         # one segment per engine: the rendezvous port is unique per concurrently running engine on a
         # host, so two tensor-parallel engines never share a control channel
         name = f"{_SHM_PREFIX}_{self.config.hccl_port}"
+        # worst case = a prefill batch shipping every token id of max_num_seqs full-length prompts
+        # (4 B each) plus their block tables and ~300 B of per-sequence state
+        cfg = self.config
+        shm_size = max(2 ** 20, cfg.max_num_seqs * (5 * cfg.max_model_len + 1024))
         if self.rank == 0:
             try:
-                self.shm = SharedMemory(name=name, create=True, size=2 ** 20)
+                self.shm = SharedMemory(name=name, create=True, size=shm_size)
             except FileExistsError:                   # stale segment from a crashed run
                 stale = SharedMemory(name=name)
                 stale.close()
                 stale.unlink()
-                self.shm = SharedMemory(name=name, create=True, size=2 ** 20)
+                self.shm = SharedMemory(name=name, create=True, size=shm_size)
             dist.barrier()
         else:
             dist.barrier()
@@ -146,7 +150,14 @@ class ModelRunner:
 
     def call(self, method, *args):
         if self.world_size > 1 and self.rank == 0 and not self.spmd:
-            blob = pickle.dumps([method, *args])
+            Sequence.wire_decode = method == "run" and not args[1]
+            try:
+                blob = pickle.dumps([method, *args], protocol=pickle.HIGHEST_PROTOCOL)
+            finally:
+                Sequence.wire_decode = False
+            if len(blob) + 4 > self.shm.size:
+                raise RuntimeError(f"step message of {len(blob)} bytes exceeds the {self.shm.size}-byte "
+                                   f"control segment (max_num_seqs x max_model_len grew after start-up?)")
             self.shm.buf[0:4] = len(blob).to_bytes(4, "little")
             self.shm.buf[4:4 + len(blob)] = blob
             for ev in self.event:

@@ -114,11 +114,15 @@ class Scheduler:
                 self.free_seq(seq, FinishReason.ABORTED)
 
     def free_seq(self, seq: Sequence, reason: FinishReason) -> None:
+        # still WAITING with blocks = a (re-)prefill in progress (chunked mode keeps the sequence at the
+        # head of ``waiting`` until its last window ran): blocks past num_computed_tokens carry
+        # hashes but no K/V yet, whether or not the sequence already had completions
+        mid_prefill = seq.status == SequenceStatus.WAITING and bool(seq.block_table)
         seq.status = SequenceStatus.FINISHED
         seq.finish_reason = reason
-        if self.chunked_prefill and seq.block_table and seq.num_computed_tokens < seq.num_prompt_tokens \
-                and seq.num_completion_tokens == 0:
-            self.block_manager.forget_uncomputed(seq, seq.num_computed_tokens)
+        computed = max(seq.num_computed_tokens, seq.num_cached_tokens)   # prefix hits hold K/V already
+        if mid_prefill and computed < len(seq):
+            self.block_manager.forget_uncomputed(seq, computed)
         self.block_manager.deallocate(seq)
 
     def postprocess(self, seqs: list[Sequence], token_ids: list[int]) -> None:

@@ -1,6 +1,7 @@
 """Request state (reference: engine/sequence.py). Host-only bookkeeping."""
 from __future__ import annotations
 
+from array import array
 from enum import Enum, auto
 from itertools import count
 
@@ -94,15 +95,28 @@ class Sequence:
     # state shipped to tensor-parallel workers each step. Unlike the reference
     # (sequence.py:116-146) block_size and the sampling fields travel too,
     # otherwise num_blocks raises on the worker side.
+    # A decode step needs only the last token (the reference makes the same cut, sequence.py:116-125);
+    # the prompt travels as packed int32 bytes, and only while the sequence is still being prefilled.
     _WIRE = ("block_size", "seq_id", "num_tokens", "num_prompt_tokens", "num_cached_tokens",
-             "block_table", "token_ids", "last_token", "status", "temperature", "max_tokens",
+             "last_token", "status", "temperature", "max_tokens",
              "ignore_eos", "greedy", "num_computed_tokens", "prefill_window")
+    wire_decode = False          # set by ModelRunner.call around the pickling of a decode batch
 
     def __getstate__(self):
-        return {k: getattr(self, k) for k in self._WIRE}
+        state = {k: getattr(self, k) for k in self._WIRE}
+        state["block_table"] = array("i", self.block_table).tobytes()
+        state["token_ids"] = None if Sequence.wire_decode else array("i", self.token_ids).tobytes()
+        return state
 
     def __setstate__(self, state):
+        table, tokens = array("i"), array("i")
+        table.frombytes(state.pop("block_table"))
+        packed = state.pop("token_ids")
+        if packed is not None:
+            tokens.frombytes(packed)
         self.__dict__.update(state)
+        self.block_table = table.tolist()
+        self.token_ids = tokens.tolist()        # empty on decode steps: workers only read last_token
         self.request_id = None
         self.finish_reason = None
         self.first_token_time = self.arrival_time = None

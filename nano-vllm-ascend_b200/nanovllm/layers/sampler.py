@@ -21,6 +21,16 @@ class Sampler(nn.Module):
         self.seed = seed
         self.step = 0
 
+    def _next_step(self, step_offset) -> int:
+        """The noise is keyed by (seed, step + *step_offset, row, index). With a device counter the
+        counter alone must be the key: a host step baked into a CUDA graph at capture differs per
+        bucket and would make two launches (bucket A at counter r, bucket B at r') collide on the
+        same effective step. Without one, the host counter advances per call."""
+        if step_offset is not None:
+            return 0
+        self.step += 1
+        return self.step
+
     def forward(self, logits: torch.Tensor, temperatures: torch.Tensor | None, greedy: bool = False,
                 out: torch.Tensor | None = None, step_offset: torch.Tensor | None = None):
         """temperatures: [real_bs] fp32; rows with temperature <= 0 (or greedy=True) take the
@@ -28,9 +38,8 @@ class Sampler(nn.Module):
         real_bs = logits.shape[0] if temperatures is None else temperatures.shape[0]
         if logits.shape[0] != real_bs:
             logits = logits[:real_bs]
-        self.step += 1
-        return ops.sample(logits, None if greedy else temperatures, seed=self.seed, step=self.step,
-                          out=out, step_offset=step_offset)
+        return ops.sample(logits, None if greedy else temperatures, seed=self.seed,
+                          step=self._next_step(step_offset), out=out, step_offset=step_offset)
 
     def shard_keys(self, logits: torch.Tensor, temperatures: torch.Tensor | None, index_offset: int,
                    greedy: bool = False, out: torch.Tensor | None = None,
@@ -42,6 +51,6 @@ class Sampler(nn.Module):
         real_bs = logits.shape[0] if temperatures is None else temperatures.shape[0]
         if logits.shape[0] != real_bs:
             logits = logits[:real_bs]
-        self.step += 1
-        return ops.sample_shard(logits, None if greedy else temperatures, seed=self.seed, step=self.step,
-                                index_offset=index_offset, out=out, step_offset=step_offset)
+        return ops.sample_shard(logits, None if greedy else temperatures, seed=self.seed,
+                                step=self._next_step(step_offset), index_offset=index_offset, out=out,
+                                step_offset=step_offset)

@@ -185,10 +185,17 @@ def test_scheduler_trace_matches_reference(name):
         sched.add(s)
     index = {s.seq_id: i for i, s in enumerate(seqs)}
     preempted = 0
+    # One documented deviation: the reference never resets num_cached_tokens, so over re-admissions
+    # of a preempted sequence its counter is the SUM of every admission's hits (and it never reads
+    # it in the runner); ours is per admission. Accumulate ours to compare like with like.
+    ref_style_cached = [0] * len(seqs)
     for step, rec in enumerate(g["steps"]):
         assert not sched.is_finished()
         batch, is_prefill = sched.schedule()
-        got = [(index[s.seq_id], list(s.block_table), s.num_cached_tokens, len(s)) for s in batch]
+        if is_prefill:
+            for s in batch:
+                ref_style_cached[index[s.seq_id]] += s.num_cached_tokens
+        got = [(index[s.seq_id], list(s.block_table), ref_style_cached[index[s.seq_id]], len(s)) for s in batch]
         assert is_prefill == rec["is_prefill"], step
         assert got == rec["seqs"], step
         sched.postprocess(batch, rec["tokens"])
@@ -275,6 +282,123 @@ def test_chunked_prefill_scheduling():
     batch, _ = sched.schedule()
     assert batch == [e] and e.num_cached_tokens == 96           # only the 6 computed blocks count as cached
     assert e.prefill_window == (96, 196)
+
+
+def test_readmission_resets_cached_tokens():
+    """A preempted sequence that had prefix hits must not carry its old num_cached_tokens into the
+    next admission (the reference accumulates it, block_manager.py:62-88, but never reads it in the
+    runner; here prepare_prefill and the chunked scheduler do)."""
+    from nanovllm.engine.block_manager import BlockManager
+    from nanovllm.engine.sequence import Sequence
+    bm = BlockManager(8, 16)
+    s = Sequence(list(range(10)), block_size=16)
+    for _ in range(3):
+        bm.allocate(s)
+        assert s.num_cached_tokens == 0
+        bm.deallocate(s)
+    a = Sequence(list(range(40)), block_size=16)
+    bm.allocate(a)
+    bm.deallocate(a)
+    for _ in range(3):                      # 2 full blocks are found in the prefix cache each time
+        bm.allocate(a)
+        assert a.num_cached_tokens == 32 < len(a)
+        bm.deallocate(a)
+
+
+def test_abort_mid_reprefill_forgets_uncomputed_blocks():
+    """Chunked mode: a preempted sequence WITH completions is re-prefilled over len(seq) tokens; if it
+    is aborted between windows, hashes of the not yet recomputed blocks must leave the prefix cache."""
+    from types import SimpleNamespace
+    from nanovllm import SamplingParams
+    from nanovllm.engine.scheduler import Scheduler
+    from nanovllm.engine.sequence import Sequence
+    cfg = SimpleNamespace(max_num_seqs=4, max_num_batched_tokens=64, eos=-1, num_kvcache_blocks=33,
+                          kvcache_block_size=16, max_model_len=4096, chunked_prefill=True)
+    sched = Scheduler(cfg)
+    sp = SamplingParams(temperature=1.0, max_tokens=50, ignore_eos=True)
+    a = Sequence(list(range(100, 228)), sp, request_id="a", block_size=16)     # 128 tokens: 2 windows
+    sched.add(a)
+    for _ in range(2):
+        batch, is_prefill = sched.schedule()
+        assert is_prefill
+        sched.postprocess(batch, [7])
+    for _ in range(20):                     # decode past another full block
+        batch, is_prefill = sched.schedule()
+        assert not is_prefill
+        sched.postprocess(batch, [7])
+    assert a.num_completion_tokens == 21
+    sched.running.remove(a)
+    sched.preempt(a)
+    # wipe the prefix cache so the re-admission has no hits and starts at token 0
+    bm = sched.block_manager
+    bm.hash_to_block_id.clear()
+    for blk in bm.blocks:
+        blk.hash, blk.token_ids = -1, []
+    batch, is_prefill = sched.schedule()
+    assert is_prefill and a.prefill_window == (0, 64) and a.num_cached_tokens == 0
+    sched.postprocess(batch, [7])
+    assert len(bm.hash_to_block_id) == 9    # allocate() registered all 9 full blocks up front
+    sched.abort_seq_group("a")
+    assert len(bm.hash_to_block_id) == 4    # only the 4 recomputed blocks stay
+    b = Sequence(a.token_ids[:], sp, block_size=16)
+    sched.add(b)
+    batch, _ = sched.schedule()
+    assert batch == [b] and b.num_cached_tokens == 64
+
+
+def test_decode_wire_message_is_small_and_complete():
+    """What rank 0 ships to tensor-parallel workers per step (model_runner.call): a decode step must
+    not carry the token history (256 x 1100 tokens pickled to 1.19 MB and overflowed the segment)."""
+    import pickle
+    from nanovllm import SamplingParams
+    from nanovllm.engine.sequence import Sequence
+    seqs = []
+    for i in range(256):
+        s = Sequence([151000 + (i + j) % 900 for j in range(1100)], SamplingParams(temperature=0.6),
+                     block_size=16)
+        s.block_table = list(range(i * 69, i * 69 + 69))
+        seqs.append(s)
+    Sequence.wire_decode = True
+    try:
+        blob = pickle.dumps(["run", seqs, False], protocol=pickle.HIGHEST_PROTOCOL)
+    finally:
+        Sequence.wire_decode = False
+    assert len(blob) < 200_000, len(blob)
+    _, got, _ = pickle.loads(blob)
+    for s, t in zip(seqs, got):
+        assert (t.seq_id, len(t), t.last_token, t.block_table, t.temperature, t.greedy, t.num_blocks) == \
+               (s.seq_id, len(s), s.last_token, s.block_table, s.temperature, s.greedy, s.num_blocks)
+        assert t.token_ids == []
+    blob = pickle.dumps(["run", seqs[:16], True], protocol=pickle.HIGHEST_PROTOCOL)
+    assert len(blob) < 16 * (4 * 1100 + 1024)
+    _, got, _ = pickle.loads(blob)
+    assert all(t.token_ids == s.token_ids for s, t in zip(seqs, got))
+
+
+def test_sampler_noise_key_is_the_device_counter_alone():
+    """With a device step counter the host step passed to the kernel is 0 for every launch, so the
+    value baked into a CUDA graph at capture cannot alias another bucket's."""
+    from nanovllm.layers.sampler import Sampler
+    s = Sampler(seed=3)
+    assert [s._next_step(object()) for _ in range(4)] == [0, 0, 0, 0] and s.step == 0
+    assert [s._next_step(None) for _ in range(3)] == [1, 2, 3]
+
+
+def test_engine_step_on_an_unschedulable_queue_raises():
+    from types import SimpleNamespace
+    from nanovllm import SamplingParams
+    from nanovllm.engine.llm_engine import LLMEngine
+    from nanovllm.engine.scheduler import Scheduler
+    from nanovllm.engine.sequence import Sequence
+    cfg = SimpleNamespace(max_num_seqs=4, max_num_batched_tokens=4096, eos=-1, num_kvcache_blocks=4,
+                          kvcache_block_size=16, max_model_len=4096)
+    eng = LLMEngine.__new__(LLMEngine)
+    eng.scheduler = Scheduler(cfg)
+    eng.model_runner = SimpleNamespace(call=lambda *a: pytest.fail("run() on an empty batch"))
+    assert eng.step() == ([], 0)            # idle
+    eng.scheduler.add(Sequence(list(range(64)), SamplingParams(), block_size=16))   # 4 blocks, pool has 3
+    with pytest.raises(RuntimeError, match="KV blocks"):
+        eng.step()
 
 
 # ------------------------------------------------------------------ N>1: TP shards on gloo
