@@ -14,8 +14,11 @@ fused norms/activation] + cuBLAS GEMMs + sampling).
   cpu_baseline  the reference's CPU path (oracle port of models/qwen3.py + torch-native
              attention) on the host cores, bounded sample of the same decode step
 
-N > 1 (torchrun): independent data-parallel replicas, no data-path collective ("weak" scaling);
-`--tp` instead shards one engine with tensor parallelism (row-parallel all-reduce over NCCL).
+N > 1 (torchrun): independent data-parallel replicas, no data-path collective ("weak" scaling) --
+the headline line -- plus a `tp` object: Qwen3-32B (BASELINE configs[3]) decode at the same batch /
+context tensor-parallel over all N GPUs (fused NVLink all-reduce + residual add + RMSNorm), with
+the all-reduce form and its latency, and the same workload at TP=1 (rank 0) for the speed-up.
+`--tp` instead makes the tensor-parallel engine the whole line ("strong" scaling).
 `--impl reference` times only the CPU reference arm.
 """
 from __future__ import annotations
@@ -90,6 +93,9 @@ def parse_args():
     ap.add_argument("--ctx", type=int, default=1024)
     ap.add_argument("--block-size", type=int, default=16)
     ap.add_argument("--tp", action="store_true", help="tensor-parallel over --gpus instead of replicas")
+    ap.add_argument("--tp-model", default="qwen3-32b",
+                    help="model of the `tp` object a multi-GPU replica run adds (BASELINE configs[3])")
+    ap.add_argument("--no-tp-block", action="store_true", help="multi-GPU replica run without the `tp` object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mem-util", type=float, default=0.7, help="gpu_memory_utilization of the engine")
     ap.add_argument("--cpu-sample-seqs", type=int, default=32)
@@ -181,26 +187,53 @@ def cpu_reference_step(n_seqs, ctx, block_size, steps, warmup, threads=None):
     return n_seqs / sec, sec
 
 
+def reference_cpu_step(n_seqs, ctx, block_size, steps, warmup, in_process):
+    """The CPU arm. With the reference archive present (oracle/_ref/, packed by oracle/stage_ref.py at
+    build time) the reference's OWN modules run: models/qwen3.py + layers/attention_torch_native.py on
+    all host cores (kind "reference"); otherwise the oracle port of the same graph (kind "port").
+    The reference registers a stub package named `nanovllm`, which is also the product's package name:
+    the GPU arm therefore runs it in a child process."""
+    from oracle import ref_runtime
+    cores = os.cpu_count() or 1
+    if ref_runtime.reference_dir() is None:
+        tps, sec = cpu_reference_step(n_seqs, ctx, block_size, steps, warmup, cores)
+        return tps, sec, "port", torch.get_num_threads()
+    if in_process:
+        tps, sec = ref_runtime.reference_decode_step(n_seqs, ctx, block_size, steps, warmup, cores)
+        return tps, sec, "reference", torch.get_num_threads()
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_runtime", "--seqs", str(n_seqs), "--ctx", str(ctx),
+                        "--block-size", str(block_size), "--steps", str(steps), "--warmup", str(warmup)],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    if r.returncode != 0:
+        raise RuntimeError("reference CPU arm failed:\n" + r.stderr[-3000:])
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    return d["tokens_per_s"], d["s_per_step"], "reference", d["threads"]
+
+
+def cpu_sample_text(kind, n_seqs, batch, ctx, steps, sec):
+    what = ("the reference's own models/qwen3.py + attention_torch_native.py (oracle/_ref archive)"
+            if kind == "reference" else
+            "oracle port of the reference CPU path (no reference archive on this box)")
+    return (f"batch {n_seqs} (of the workload's {batch} sequences), one full 28-layer decode step at "
+            f"ctx={ctx}, {steps} timed steps of {sec:.2f} s each; {what}")
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # bounded sample: as many of the workload's sequences as keep the whole run near a minute
     # (about 0.07 s per sequence-step on 8 host cores)
     n_seqs = max(1, min(32, args.batch, int(600 / (steps + warmup))))
     args.cpu_sample_seqs = n_seqs
-    tps, sec = cpu_reference_step(n_seqs, args.ctx, args.block_size, steps, warmup)
+    tps, sec, kind, cores = reference_cpu_step(n_seqs, args.ctx, args.block_size, steps, warmup, True)
     line = {
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.cpu_sample_seqs} of {args.batch} sequences, full 28-layer decode "
-                                   f"step at ctx={args.ctx} (oracle port of the reference CPU path; the "
-                                   f"Python reference itself cannot travel to the GPU box)"},
+        "config": dict(workload_config(args, 1), cpu_sample_batch=n_seqs),
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": cpu_sample_text(kind, n_seqs, args.batch, args.ctx, steps, sec)},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -222,6 +255,216 @@ def dbg(rank, *a):
         print(f"[bench rank{rank} {time.strftime('%X')}]", *a, file=sys.stderr, flush=True)
 
 
+class Group:
+    """The ranks a measurement spans: every torchrun rank (replicas, TP=N) or this rank alone (the
+    TP=1 comparison run rank 0 makes while the others wait)."""
+
+    def __init__(self, world):
+        self.world = world
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def decode_workload(llm, group, B, ctx, K, W, prompt_seed, rank):
+    """The workload of BASELINE configs[1] on one engine: submit B prompts of `ctx` tokens at t = 0,
+    prefill (TTFT), W warm-up decode steps, K decode steps through LLM.step() (e2e: pinned H2D of the
+    step metadata + D2H of the sampled ids inside the timed region), then K replays of the captured
+    step with its inputs resident (device). Times are CUDA events, max over the group's ranks."""
+    from nanovllm import SamplingParams
+    runner = llm.model_runner
+    rnd = random.Random(prompt_seed)
+    prompts = [[rnd.randint(0, 10000) for _ in range(ctx)] for _ in range(B)]
+    sp = SamplingParams(temperature=0.6, ignore_eos=True, max_tokens=W + K + 8)
+    group.barrier()
+    t_submit = time.perf_counter()
+    seqs = [llm.add_request(p, sp) for p in prompts]
+    prefill_steps = 0
+    while llm.scheduler.waiting:
+        llm.step()
+        prefill_steps += 1
+    ttfts = sorted((s.first_token_time - t_submit) * 1e3 for s in seqs)
+    dbg(rank, 'prefill done')
+    for _ in range(W):
+        llm.step()
+    group.barrier()
+    h2d0, d2h0 = runner.h2d_bytes, runner.d2h_bytes
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        out, ntok = llm.step()
+        assert ntok == -B, f"decode batch shrank to {-ntok}"
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_s = group.max(max(e0.elapsed_time(e1) / 1e3, time.perf_counter() - t0))
+    dbg(rank, 'e2e done')
+    graph = runner.graphs[B]
+    for _ in range(W):
+        graph.replay()
+    group.barrier()
+    e0.record()
+    for _ in range(K):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    dev_s = group.max(e0.elapsed_time(e1) / 1e3)
+    del graph
+    dbg(rank, 'replay done')
+    return {"e2e_s": e2e_s, "dev_s": dev_s, "ttfts": ttfts, "prefill_steps": prefill_steps,
+            "h2d_per": (runner.h2d_bytes - h2d0) / K, "d2h_per": (runner.d2h_bytes - d2h0) / K,
+            "launches": runner.launches_per_graph.get(B, 0) * K, "ctx_now": ctx + W + K}
+
+
+def attention_roofline(runner, group, B, K, tpw, fp8, peak, peak_src):
+    """The dominant kernel alone: one launch per layer over that layer's own cache (all layers = tens
+    of GB per pass, cold in L2), CUDA events on the launching stream."""
+    from nanovllm import ops
+    spec = runner.spec
+    Hq, Hkv, D = spec.num_heads // tpw, max(1, spec.num_kv_heads // tpw), spec.head_dim
+    q = torch.randn(B, Hq, D, device="cuda", dtype=runner.dtype)
+    o = torch.empty(B, Hq * D, device="cuda", dtype=runner.dtype)
+    ws = ops.decode_workspace(B, Hq, Hkv, D, q.device)
+    L = spec.num_layers
+    attn_fn = ops.paged_decode_attn_fp8 if fp8 else ops.paged_decode_attn
+
+    def attn_pass():
+        for layer in range(L):
+            attn_fn(q, runner.kv_cache[0, layer], runner.kv_cache[1, layer],
+                    runner.d_tables[:B], runner.d_ctx[:B], D ** -0.5, Hkv, out=o, workspace=ws)
+    for _ in range(3):
+        attn_pass()
+    group.barrier()
+    reps = max(4, min(K, 32))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        attn_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    launch_s = e0.elapsed_time(e1) / 1e3 / (reps * L)
+    ctx_sum = int(runner.d_ctx[:B].sum().item())
+    nbytes = ctx_sum * 2 * Hkv * D * runner.kv_cache.dtype.itemsize       # algorithmic bytes / launch
+    achieved = nbytes / launch_s / 1e9
+    traffic = traffic_ctx = None
+    tpath = os.path.join(ROOT, "profiles", "decode_attn_traffic.json")
+    if os.path.exists(tpath) and not fp8 and tpw == 1:
+        with open(tpath) as f:
+            t = json.load(f)
+        # the ncu capture was taken at its own context length: scale its bytes/token to this run's
+        per_token = t["dram_bytes_per_launch"] / t["context_tokens_per_launch"]
+        traffic, traffic_ctx = per_token * ctx_sum, t["context_tokens_per_launch"] // B
+    return {"bound": "hbm", "kernel": "paged_decode_fp8_kernel" if fp8 else "paged_decode_kernel",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": None if traffic is None else
+            f"ncu dram__bytes_read+write per cached token at ctx {traffic_ctx} (profiles/"
+            f"decode_attn_traffic.json) x this run's {ctx_sum} cached tokens per launch",
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes,
+            "us_per_launch": launch_s * 1e6, "layers": L}
+
+
+def release(llm):
+    """Tear an engine down and give its memory back (the caller must hold no other reference to the
+    runner): graphs, KV cache, weights, peer-memory regions."""
+    import gc
+    llm.exit()
+    del llm
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
+def allreduce_microbench(runner, rows, reps=200):
+    """The layer's collective alone: the fused all-reduce + residual add + RMSNorm kernel over NVLink
+    (or NCCL all-reduce + the add-RMSNorm kernel when the fused path does not take the shape)."""
+    import torch.distributed as dist
+    from nanovllm import ops
+    from nanovllm.comm import get_comm
+    hidden = runner.spec.hidden_size
+    comm = get_comm()
+    res = torch.zeros(rows, hidden, dtype=runner.dtype, device="cuda")
+    w = torch.ones(hidden, dtype=runner.dtype, device="cuda")
+    out = torch.empty_like(res)
+    form = comm.mode(rows, hidden, res.element_size()) if comm is not None else None
+
+    def one():
+        if form is not None:
+            comm.partial_buffer(rows, hidden, runner.dtype)
+            comm.allreduce_add_rmsnorm(out, res, w, 1e-6)
+        else:
+            dist.all_reduce(out)
+            ops.add_rmsnorm(out, res, w, 1e-6)
+    for _ in range(10):
+        one()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    return form or "nccl", e0.elapsed_time(e1) * 1e3 / reps
+
+
+def tp_block(args, rank, world, K, W, peak, peak_src):
+    """BASELINE configs[3]: Qwen3-32B decode, batch 256, ctx 1024, tensor-parallel over ALL `world`
+    GPUs of this run, next to the same workload at TP=1 (rank 0 alone, the other ranks wait), so the
+    driver's scaling record carries the north_star's "TP=8 >= 6x TP=1" figure."""
+    import torch.distributed as dist
+    from nanovllm import LLM
+    B, ctx = args.batch, args.ctx
+    kw = dict(kvcache_block_size=args.block_size, max_num_seqs=B, max_model_len=4096,
+              max_num_batched_tokens=16384, distributed_launch="env", gpu_memory_utilization=0.88,
+              graph_batch_sizes=(B,), seed=0)
+    out = {"model": args.tp_model, "tp": world, "batch": B, "ctx": ctx}
+    llm = LLM(args.tp_model, tensor_parallel_size=world, **kw)
+    runner = llm.model_runner
+    r = decode_workload(llm, Group(world), B, ctx, K, W, 0, rank)
+    form, ar_us = allreduce_microbench(runner, B)
+    roof = attention_roofline(runner, Group(world), B, K, world, False, peak, peak_src)
+    L, spec = runner.spec.num_layers, runner.spec
+    weight_bytes = sum(p.numel() * p.element_size() for p in runner.model.parameters())
+    step_bytes = weight_bytes + roof["algorithmic_bytes_per_launch"] * L
+    out.update({
+        "tokens_per_s": B * K / r["dev_s"], "ms_per_step": r["dev_s"] / K * 1e3,
+        "e2e_tokens_per_s": B * K / r["e2e_s"], "e2e_ms_per_step": r["e2e_s"] / K * 1e3,
+        "ttft_p50_ms": r["ttfts"][len(r["ttfts"]) // 2], "gpu_launches_per_step": r["launches"] // K,
+        "allreduce_form": form, "allreduce_us": ar_us, "allreduces_per_step": 2 * L,
+        "allreduce_message_bytes": B * spec.hidden_size * 2,
+        "sampling": "vocab-sharded keys + 8 B/row MAX all-reduce" if runner.sharded_sampling else
+                    "logits gathered on rank 0",
+        "attention_us_per_layer": roof["us_per_launch"], "attention_frac_of_hbm_peak": roof["frac"],
+        "per_rank_bytes_per_step": step_bytes,
+        "per_rank_hbm_floor_ms": step_bytes / (peak * 1e9) * 1e3,
+    })
+    del runner
+    release(llm)
+    dist.barrier()
+    if rank == 0:
+        llm = LLM(args.tp_model, tensor_parallel_size=1, **kw)
+        r1 = decode_workload(llm, Group(1), B, ctx, K, W, 0, rank)
+        out.update({"tp1_tokens_per_s": B * K / r1["dev_s"], "tp1_ms_per_step": r1["dev_s"] / K * 1e3,
+                    "tp1_e2e_tokens_per_s": B * K / r1["e2e_s"]})
+        out["speedup_vs_tp1"] = out["tokens_per_s"] / out["tp1_tokens_per_s"]
+        out["e2e_speedup_vs_tp1"] = out["e2e_tokens_per_s"] / out["tp1_e2e_tokens_per_s"]
+        release(llm)
+    dist.barrier()
+    return out
+
+
 def main():
     args = parse_args()
     if os.environ.get("B200_BENCH_DEBUG"):
@@ -240,7 +483,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from nanovllm import LLM, SamplingParams, ops
+    from nanovllm import LLM
     K, W, B, ctx = args.steps, max(3, args.warmup), args.batch, args.ctx
     max_len = ctx + W + K + 16
     llm = LLM(args.model, kvcache_block_size=args.block_size, max_num_seqs=B,
@@ -249,152 +492,63 @@ def main():
               gpu_memory_utilization=args.mem_util, kv_cache_dtype=args.kv_cache_dtype, seed=0)
     runner = llm.model_runner
     spec = runner.spec
-    rnd = random.Random(rank if not args.tp else 0)
-    prompts = [[rnd.randint(0, 10000) for _ in range(ctx)] for _ in range(B)]
-    sp = SamplingParams(temperature=0.6, ignore_eos=True, max_tokens=W + K + 8)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    group = Group(world)
     clocks = ClockSampler(local)
     dbg(rank, 'engine built')
-    # ---- phase 1: submit everything at t=0, prefill (TTFT)
-    barrier()
+    group.barrier()
     clocks.start()
-    t_submit = time.perf_counter()
-    seqs = [llm.add_request(p, sp) for p in prompts]
-    prefill_steps = 0
-    while llm.scheduler.waiting:
-        llm.step()
-        prefill_steps += 1
-    ttfts = sorted((s.first_token_time - t_submit) * 1e3 for s in seqs)
-    ttft_p50 = ttfts[len(ttfts) // 2]
-    prefill_s = ttfts[-1] / 1e3
-
-    dbg(rank, 'prefill done')
-    # ---- phase 2: e2e decode through the public API (host buffers, H2D + D2H inside)
-    for _ in range(W):
-        llm.step()
-    barrier()
-    h2d0, d2h0 = runner.h2d_bytes, runner.d2h_bytes
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        out, ntok = llm.step()
-        assert ntok == -B, f"decode batch shrank to {-ntok}"
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_wall = time.perf_counter() - t0
-    e2e_s = max(e0.elapsed_time(e1) / 1e3, e2e_wall)
-    e2e_s = max_over_ranks(e2e_s)
-    h2d_per = (runner.h2d_bytes - h2d0) / K
-    d2h_per = (runner.d2h_bytes - d2h0) / K
-    ctx_now = ctx + W + K            # context length the resident buffers now describe
-
-    dbg(rank, 'e2e done')
-    # ---- phase 3: device-only: replay the captured step with its inputs resident in HBM
-    graph = runner.graphs[B]
-    for _ in range(W):
-        graph.replay()
-    barrier()
-    e0.record()
-    for _ in range(K):
-        graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    dev_s = max_over_ranks(e0.elapsed_time(e1) / 1e3)
-    launches = runner.launches_per_graph.get(B, 0) * K
-
-    dbg(rank, 'replay done')
-    # ---- phase 4: the dominant kernel alone, all layers' caches (cold in L2), CUDA events
-    tpw = world if args.tp else 1
-    Hq, Hkv, D = spec.num_heads // tpw, max(1, spec.num_kv_heads // tpw), spec.head_dim
-    q = torch.randn(B, Hq, D, device="cuda", dtype=runner.dtype)
-    o = torch.empty(B, Hq * D, device="cuda", dtype=runner.dtype)
-    ws = ops.decode_workspace(B, Hq, Hkv, D, q.device)
-    L = spec.num_layers
-
-    attn_fn = ops.paged_decode_attn if args.kv_cache_dtype == "auto" else ops.paged_decode_attn_fp8
-
-    def attn_pass():
-        for layer in range(L):
-            attn_fn(q, runner.kv_cache[0, layer], runner.kv_cache[1, layer],
-                    runner.d_tables[:B], runner.d_ctx[:B], D ** -0.5, Hkv, out=o, workspace=ws)
-    for _ in range(3):
-        attn_pass()
-    barrier()
-    reps = max(4, min(K, 32))
-    e0.record()
-    for _ in range(reps):
-        attn_pass()
-    e1.record()
-    torch.cuda.synchronize()
-    attn_launch_s = e0.elapsed_time(e1) / 1e3 / (reps * L)
+    r = decode_workload(llm, group, B, ctx, K, W, rank if not args.tp else 0, rank)
+    peak, peak_src = peaks()
+    fp8 = args.kv_cache_dtype != "auto"
+    roof = attention_roofline(runner, group, B, K, world if args.tp else 1, fp8, peak, peak_src)
     dbg(rank, 'attn loop done')
     clk = clocks.stop()
-    ctx_sum = int(runner.d_ctx[:B].sum().item())
-    attn_bytes = ctx_sum * 2 * Hkv * D * runner.kv_cache.dtype.itemsize  # algorithmic bytes / launch
-    peak, peak_src = peaks()
-    achieved = attn_bytes / attn_launch_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "decode_attn_traffic.json")
-    if os.path.exists(tpath) and args.kv_cache_dtype == "auto":
-        with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
 
-    value = world * B * K / dev_s if not args.tp else B * K / dev_s
-    e2e_val = world * B * K / e2e_s if not args.tp else B * K / e2e_s
+    ttfts, dev_s, e2e_s = r["ttfts"], r["dev_s"], r["e2e_s"]
+    prefill_s = ttfts[-1] / 1e3
+    engines = 1 if args.tp else world
+    value = engines * B * K / dev_s
     # KV-read roofline of the whole step at the measured peak (what `value` is bounded by)
-    step_kv_bytes = attn_bytes * L
+    step_kv_bytes = roof["algorithmic_bytes_per_launch"] * roof["layers"]
+    roof["step_kv_roofline_tokens_per_s"] = B / (step_kv_bytes / (peak * 1e9))
+    roof["step_frac_of_kv_roofline"] = (B * K / dev_s) / roof["step_kv_roofline_tokens_per_s"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak" if not args.tp else "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, random token ids)",
-        "config": dict(workload_config(args, world), ctx_during_timing=[ctx + W, ctx_now]),
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_per, "d2h_bytes_per_step": d2h_per,
-                "ms_per_step": e2e_s / K * 1e3},
-        "ttft_p50_ms": ttft_p50, "ttft_max_ms": ttfts[-1], "prefill_steps": prefill_steps,
-        "prefill_tokens_per_s": world * B * ctx / prefill_s if not args.tp else B * ctx / prefill_s,
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "paged_decode_kernel" if args.kv_cache_dtype == "auto"
-                     else "paged_decode_fp8_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": attn_bytes,
-                     "us_per_launch": attn_launch_s * 1e6,
-                     "step_kv_roofline_tokens_per_s": B / (step_kv_bytes / (peak * 1e9)),
-                     "step_frac_of_kv_roofline": (B * K / dev_s) / (B / (step_kv_bytes / (peak * 1e9)))},
+        "config": dict(workload_config(args, world), ctx_during_timing=[ctx + W, r["ctx_now"]]),
+        "e2e": {"value": engines * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": r["h2d_per"],
+                "d2h_bytes_per_step": r["d2h_per"], "ms_per_step": e2e_s / K * 1e3},
+        "ttft_p50_ms": ttfts[len(ttfts) // 2], "ttft_max_ms": ttfts[-1], "prefill_steps": r["prefill_steps"],
+        "prefill_tokens_per_s": engines * B * ctx / prefill_s,
+        "gpu_launches": r["launches"],
+        "roofline": roof,
         "clocks": clk,
     }
     if getattr(spec, "num_experts", 0):
         line["moe_roofline"] = moe_expert_roofline(runner, B, peak)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "qwen3-0.6b":
-        tps, sec = cpu_reference_step(args.cpu_sample_seqs, ctx, args.block_size, 3, 1)
-        line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{args.cpu_sample_seqs} of {B} sequences, one full 28-layer decode "
-                                          f"step at ctx={ctx}, 3 timed steps of {sec:.1f} s each"}
     dbg(rank, 'before exit')
-    llm.exit()
+    del runner
+    release(llm)
     dbg(rank, 'after exit')
+    if world > 1 and not args.tp and not args.no_tp_block:
+        # the replicas above say nothing about the collective design: the same run also measures the
+        # tensor-parallel path (BASELINE configs[3]) over all `world` GPUs, with its TP=1 comparison
+        try:
+            line["tp"] = tp_block(args, rank, world, K, W, peak, peak_src)
+        except Exception as e:            # symmetric failures only (OOM on every rank); reported, not hidden
+            line["tp"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "qwen3-0.6b":
+        tps, sec, kind, cores = reference_cpu_step(args.cpu_sample_seqs, ctx, args.block_size, 3, 1, False)
+        line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": cpu_sample_text(kind, args.cpu_sample_seqs, B, ctx, 3, sec)}
+        line["config"]["cpu_sample_batch"] = args.cpu_sample_seqs
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        # destroy_process_group() can block for minutes once CUDA graphs that embedded NCCL kernels
-        # have been replayed; everything is measured and printed, so leave without the teardown
-        dist.barrier()
         sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -231,14 +231,6 @@ int b200_sample_shard(int64_t* out_keys, const void* logits, const float* temper
                       int32_t vocab_local, int64_t logits_stride, int32_t index_offset, uint64_t seed,
                       uint64_t step, const int64_t* step_offset, int32_t dtype, b200_stream_t stream);
 
-/* L2 weight prefetch (experiment; the Python side enables it with B200_DECODE_L2_PREFETCH=1):
- * cp.async.bulk.prefetch.L2 over up to 8 byte ranges (16-byte aligned; HOST arrays of device
- * pointers / sizes), optionally with an evict-last policy. Meant for a side stream running next
- * to the HBM-streaming decode attention kernel, so that the latency-bound M<=256 GEMMs that follow
- * find their weights in the 126 MB L2. No reference counterpart; no semantic effect. */
-int b200_l2_prefetch(const void* const* ptrs, const int64_t* bytes, int32_t n, int32_t evict_last,
-                     int32_t num_ctas, b200_stream_t stream);
-
 /* ---------------------------------------------------------------------------------
  * MoE  sparse mixture-of-experts MLP: routing, dispatch plan, expert GEMMs, combine.
  * Replaces: Qwen3MoeSparseMoeBlock.forward                            models/qwen3_moe.py:146-186

@@ -101,63 +101,3 @@ extern "C" int b200_reshape_and_cache_2d(const void* key, const void* value, voi
                               num_kv_heads, head_dim, key_stride, value_stride, num_blocks,
                               block_size, dtype, (cudaStream_t)stream);
 }
-
-// ---------------------------------------------------------------------------------------------
-// L2 weight prefetch (experiment, opt-in from Python: B200_DECODE_L2_PREFETCH=1).
-// A decode layer's GEMMs at M = 256 are latency-bound, not bandwidth-bound: 8-65 MB of weights
-// each, read through a k-loop whose iterations wait on HBM latency (7 us for 8.4 MB = 1.1 TB/s).
-// The attention kernel before them streams ~1 GB with an evict-first policy and needs no L2
-// capacity, so this kernel -- launched on a side stream next to it -- pulls the layer's next
-// weight matrices into the 126 MB L2 (cp.async.bulk.prefetch.L2, evict-last) for the GEMMs to
-// find there. No semantic effect; the same HBM bytes are read once either way.
-namespace b200 {
-constexpr int kMaxPrefetchRanges = 8;
-struct L2PrefetchParams {
-  const char* ptr[kMaxPrefetchRanges];
-  long long bytes[kMaxPrefetchRanges];
-  int n, evict_last;
-};
-__global__ void __launch_bounds__(128)
-l2_prefetch_kernel(const L2PrefetchParams p) {
-  constexpr uint32_t kChunk = 4096;
-  uint64_t pol = 0;
-  if (p.evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (int r = 0; r < p.n; ++r) {
-    const long long chunks = (p.bytes[r] + kChunk - 1) / kChunk;
-    for (long long c = tid; c < chunks; c += nthreads) {
-      const char* a = p.ptr[r] + c * kChunk;
-      const long long left = p.bytes[r] - c * kChunk;
-      const uint32_t n = (uint32_t)(left < kChunk ? (left & ~15ll) : kChunk);
-      if (n == 0) continue;
-      if (p.evict_last)
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(a), "r"(n), "l"(pol)
-                     : "memory");
-      else
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
-    }
-  }
-}
-}  // namespace b200
-
-extern "C" int b200_l2_prefetch(const void* const* ptrs, const int64_t* bytes, int32_t n,
-                                int32_t evict_last, int32_t num_ctas, b200_stream_t stream) {
-  using namespace b200;
-  B200_RETURN_IF(n < 0 || n > kMaxPrefetchRanges || num_ctas < 0, B200_ERR_BAD_SHAPE);
-  if (n == 0) return B200_OK;
-  B200_RETURN_IF(!ptrs || !bytes, B200_ERR_NULL_POINTER);
-  L2PrefetchParams p;
-  p.n = n, p.evict_last = evict_last ? 1 : 0;
-  for (int i = 0; i < n; ++i) {
-    B200_RETURN_IF(!ptrs[i], B200_ERR_NULL_POINTER);
-    B200_RETURN_IF(bytes[i] < 0, B200_ERR_BAD_SHAPE);
-    B200_RETURN_IF(!aligned16(ptrs[i]), B200_ERR_MISALIGNED);
-    p.ptr[i] = reinterpret_cast<const char*>(ptrs[i]);
-    p.bytes[i] = bytes[i];
-  }
-  for (int i = n; i < kMaxPrefetchRanges; ++i) p.ptr[i] = nullptr, p.bytes[i] = 0;
-  // plain launch (no PDL attribute): it is the first kernel of a forked side stream
-  l2_prefetch_kernel<<<num_ctas > 0 ? num_ctas : 16, 128, 0, (cudaStream_t)stream>>>(p);
-  return finish_launch();
-}

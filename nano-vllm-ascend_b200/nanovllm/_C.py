@@ -57,7 +57,6 @@ PROTOTYPES = {
     "b200_silu_and_mul": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b200_sample_shard": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32,
                                     c_uint64, c_uint64, c_void_p, c_int32, c_void_p]),
-    "b200_l2_prefetch": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b200_moe_route": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
                                  c_int32, c_void_p]),
     "b200_moe_align": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,

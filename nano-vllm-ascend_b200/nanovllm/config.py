@@ -91,6 +91,7 @@ class Config:
     # additions (all optional; defaults keep the reference behaviour)
     seed: int = 0                      # random-init / sampler seed
     norm_jitter: float = 0.0           # random-init only
+    init_std: float = 0.02             # random-init only: std of the matrices
     init_device: str = "auto"          # random-init: "cpu" (name-seeded, == oracle), "cuda", or "auto"
                                        # (cuda above 2e9 parameters)
     load_weights: bool | None = None   # None: load iff *.safetensors exist under `model`
@@ -100,6 +101,11 @@ class Config:
     chunked_prefill: bool = False      # split prompts over several prefill steps when the token budget
                                        # (max_num_batched_tokens) runs out; later chunks attend to the
                                        # earlier ones through the paged cache
+    graph_batch_sizes: tuple | None = None   # decode batch sizes to capture CUDA graphs for (None: the
+                                       # default ladder 1, 2, 4, ..., max_num_seqs; max_num_seqs is always added)
+    tp_shard_emulation: int = 0        # profiling aid: N > 1 builds rank 0's shard of an N-way tensor-parallel
+                                       # model in ONE process, collectives skipped (per-rank kernel timeline of a
+                                       # TP=N step on one GPU; outputs are meaningless). tensor_parallel_size stays 1
     kv_cache_dtype: str = "auto"       # "auto": the model dtype (reference behaviour); "fp8" /
                                        # "fp8_e4m3": e4m3 bytes, per-tensor scale 1.0
     device = "cuda"

@@ -65,7 +65,12 @@ class ModelRunner:
                 dist.init_process_group("nccl", f"tcp://127.0.0.1:{config.hccl_port}",
                                         world_size=self.world_size, rank=rank)
         from ..layers.linear import set_tp_world
-        set_tp_world(0, 1) if self.world_size == 1 else set_tp_world(None)
+        self.shard_world = self.world_size
+        if self.world_size == 1 and config.tp_shard_emulation > 1:
+            self.shard_world = config.tp_shard_emulation
+            set_tp_world(0, self.shard_world, collectives=False)
+        else:
+            set_tp_world(0, 1) if self.world_size == 1 else set_tp_world(None)
         local = int(os.environ.get("LOCAL_RANK", rank)) if self.spmd else rank
         self.device = torch.device("cuda", local if self.world_size > 1 or self.spmd else
                                    torch.cuda.current_device())
@@ -90,9 +95,9 @@ class ModelRunner:
             n_params = sum(p.numel() for p in self.model.parameters())
             on_device = config.init_device == "cuda" or (config.init_device == "auto" and n_params > 2e9)
             if on_device:
-                device_init(self.model, seed=config.seed)
+                device_init(self.model, seed=config.seed, std=config.init_std)
             else:
-                seeded_init(self.model, seed=config.seed, norm_jitter=config.norm_jitter)
+                seeded_init(self.model, seed=config.seed, norm_jitter=config.norm_jitter, std=config.init_std)
         self.model.eval()
         self.spec = self.model.spec
         self.comm = None
@@ -201,7 +206,7 @@ class ModelRunner:
 
     def _allocate_kv_cache(self):
         cfg, spec = self.config, self.spec
-        kv_heads = max(1, spec.num_kv_heads // self.world_size)    # < 1: kv heads replicated (linear.py)
+        kv_heads = max(1, spec.num_kv_heads // self.shard_world)    # < 1: kv heads replicated (linear.py)
         # e4m3 caches are kept as raw bytes (uint8); the attention layers dispatch on that dtype
         cache_dtype = self.dtype if cfg.kv_cache_dtype == "auto" else torch.uint8
         block_bytes = 2 * spec.num_layers * self.block_size * kv_heads * spec.head_dim * cache_dtype.itemsize
@@ -385,9 +390,9 @@ class ModelRunner:
 
     def _buckets(self) -> list[int]:
         top = self.config.max_num_seqs
-        out = [b for b in (1, 2, 4, 8, 16, 32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 448, 512)
-               if b < top]
-        return out + [top]
+        ladder = self.config.graph_batch_sizes or (1, 2, 4, 8, 16, 32, 64, 96, 128, 160, 192, 224, 256,
+                                                   320, 384, 448, 512)
+        return sorted({b for b in ladder if 0 < b < top}) + [top]
 
     @torch.inference_mode()
     def _capture_decode_graphs(self):

@@ -7,7 +7,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..utils.context import get_context
-from .linear import tp_rank_size
+from .linear import tp_collectives, tp_rank_size
 
 
 class VocabParallelEmbedding(nn.Module):
@@ -34,7 +34,8 @@ class VocabParallelEmbedding(nn.Module):
         mine = (x >= self.vocab_start_idx) & (x < self.vocab_end_idx)
         y = F.embedding(mine * (x - self.vocab_start_idx), self.weight)
         y = mine.unsqueeze(1) * y
-        dist.all_reduce(y)
+        if tp_collectives():
+            dist.all_reduce(y)
         return y
 
 
@@ -60,7 +61,7 @@ class ParallelLMHead(VocabParallelEmbedding):
         if context.is_prefill:
             x = x[(context.cu_seqlens_q[1:] - 1).long()].contiguous()
         logits = F.linear(x, self.weight)
-        if self.tp_size > 1:
+        if self.tp_size > 1 and tp_collectives():
             parts = [torch.empty_like(logits) for _ in range(self.tp_size)] if self.tp_rank == 0 else None
             dist.gather(logits, parts, 0)
             logits = torch.cat(parts, -1) if self.tp_rank == 0 else None

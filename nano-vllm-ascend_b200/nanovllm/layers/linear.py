@@ -14,14 +14,23 @@ from torch import nn
 
 
 _TP_OVERRIDE: tuple[int, int] | None = None
+_TP_COLLECTIVES = True
 
 
-def set_tp_world(rank: int | None, size: int | None = None) -> None:
+def set_tp_world(rank: int | None, size: int | None = None, collectives: bool = True) -> None:
     """Pin the tensor-parallel (rank, size) the layers shard by. ``None`` restores the
     reference behaviour (the default process group's rank/size, linear.py:23-24). The runner
-    pins (0, 1) for data-parallel replicas that share a process group only for timing."""
-    global _TP_OVERRIDE
+    pins (0, 1) for data-parallel replicas that share a process group only for timing.
+    ``collectives=False`` (Config.tp_shard_emulation, a profiling aid): build one rank's shard of a
+    size-way model in a single process and skip every collective -- the per-rank kernel timeline of
+    a TP=8 step on one GPU; the numbers it computes are meaningless."""
+    global _TP_OVERRIDE, _TP_COLLECTIVES
     _TP_OVERRIDE = None if rank is None else (int(rank), int(size))
+    _TP_COLLECTIVES = bool(collectives)
+
+
+def tp_collectives() -> bool:
+    return _TP_COLLECTIVES
 
 
 def tp_rank_size() -> tuple[int, int]:
@@ -153,6 +162,6 @@ class RowParallelLinear(LinearBase):
                     torch.addmm(bias, x, self.weight.t(), out=buf)
                 return buf          # partial sum; RMSNorm(x, residual) completes the all-reduce
         y = F.linear(x, self.weight, bias)
-        if self.tp_size > 1:
+        if self.tp_size > 1 and _TP_COLLECTIVES:
             dist.all_reduce(y)
         return y

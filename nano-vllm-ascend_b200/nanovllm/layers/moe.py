@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .linear import ReplicatedLinear, tp_rank_size
+from .linear import ReplicatedLinear, tp_collectives, tp_rank_size
 
 
 class _ExpertMatrix(nn.Module):
@@ -98,6 +98,6 @@ class SparseMoeBlock(nn.Module):
                 out = comm.partial_buffer(tokens, hidden, x.dtype)   # RMSNorm completes the all-reduce
                 return ops.moe_experts(x, self.w13, self.w2, topk_ids, topk_w, plan, out=out)
         y = ops.moe_experts(x, self.w13, self.w2, topk_ids, topk_w, plan)
-        if self.ep_size > 1:
+        if self.ep_size > 1 and tp_collectives():
             dist.all_reduce(y)
         return y

@@ -14,7 +14,6 @@ o GEMM -> fused add+RMSNorm -> gate_up GEMM -> fused SiluAndMul -> down GEMM.
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass
 
 import torch
@@ -29,24 +28,6 @@ from ..layers.linear import (MergedColumnParallelLinear, QKVParallelLinear, RowP
                              tp_rank_size)
 from ..layers.rotary_embedding import RotaryEmbedding, get_rope
 from ..utils.context import get_context
-
-
-# Experiment (off by default): while the HBM-streaming decode attention kernel runs, a side stream
-# prefetches the weights of the GEMMs that follow it into L2 (csrc/kv_scatter.cu, b200_l2_prefetch).
-# "1": evict-last policy, "2": default policy.
-_L2_PREFETCH = os.environ.get("B200_DECODE_L2_PREFETCH", "0")
-_L2_PREFETCH_CTAS = int(os.environ.get("B200_DECODE_L2_PREFETCH_CTAS", "16"))
-_side_streams: dict = {}
-# Experiment (off by default): decode-sized gate|up GEMM + SiluAndMul as ONE tcgen05 kernel
-# (ops.gate_up_silu_umma) instead of cuBLAS + silu_and_mul.
-_FUSED_GATE_UP = os.environ.get("B200_FUSED_GATE_UP", "0") == "1"
-
-
-def _side_stream(device) -> torch.cuda.Stream:
-    s = _side_streams.get(device)
-    if s is None:
-        s = _side_streams[device] = torch.cuda.Stream(device=device)
-    return s
 
 
 @dataclass
@@ -111,24 +92,6 @@ class DecoderAttention(nn.Module):
             self.k_norm = RMSNorm(self.head_dim, eps=spec.rms_eps)
         else:
             self.q_norm = self.k_norm = None
-        self.prefetch_next: list = []        # weights used right after this layer's attention (set by the model)
-        self._prefetch = None
-
-    def _attend(self, attn, q, k, v, ctx):
-        """Attention, optionally with the L2 prefetch of the following GEMMs' weights forked onto a
-        side stream for the duration of the (decode) attention kernel."""
-        if _L2_PREFETCH == "0" or ctx.is_prefill or not self.prefetch_next:
-            return attn(q, k, v, kv_stored=not attn.fp8_cache)
-        if self._prefetch is None:
-            self._prefetch = ops.L2Prefetch(self.prefetch_next, evict_last=_L2_PREFETCH == "1",
-                                            num_ctas=_L2_PREFETCH_CTAS)
-        main = torch.cuda.current_stream()
-        side = _side_stream(q.device)
-        side.wait_stream(main)               # fork (inside graph capture: a parallel branch)
-        self._prefetch.launch(side)
-        o = attn(q, k, v, kv_stored=not attn.fp8_cache)
-        main.wait_stream(side)               # join
-        return o
 
     def forward(self, positions: torch.Tensor, hidden_states: torch.Tensor) -> torch.Tensor:
         qkv = self.qkv_proj(hidden_states)
@@ -146,7 +109,7 @@ class DecoderAttention(nn.Module):
         q = qkv[:, :self.q_size].unflatten(1, (self.num_heads, self.head_dim))
         k = qkv[:, self.q_size:self.q_size + self.kv_size].unflatten(1, (self.num_kv_heads, self.head_dim))
         v = qkv[:, self.q_size + self.kv_size:].unflatten(1, (self.num_kv_heads, self.head_dim))
-        o = self._attend(attn, q, k, v, ctx)              # fp8 cache: attn runs the quantising scatter
+        o = attn(q, k, v, kv_stored=not attn.fp8_cache)   # fp8 cache: attn runs the quantising scatter
         return self.o_proj(o)
 
 
@@ -160,11 +123,7 @@ class DecoderMLP(nn.Module):
         self.act_fn = SiluAndMul()
 
     def forward(self, x):
-        gu = self.gate_up_proj
-        if (_FUSED_GATE_UP and x.dim() == 2 and x.shape[0] <= 512 and gu.bias is None and x.is_contiguous()
-                and x.shape[1] % 64 == 0 and gu.weight.shape[0] % 128 == 0):
-            return self.down_proj(ops.gate_up_silu_umma(x, gu.weight))
-        return self.down_proj(self.act_fn(gu(x)))
+        return self.down_proj(self.act_fn(self.gate_up_proj(x)))
 
 
 class DecoderLayer(nn.Module):
@@ -212,15 +171,6 @@ class DecoderModel(nn.Module):
                          RotaryEmbedding(spec.head_dim, spec.head_dim, spec.max_position, spec.rope_theta), i)
             for i in range(spec.num_layers)])
         self.norm = RMSNorm(spec.hidden_size, eps=spec.rms_eps)
-        for i, layer in enumerate(self.layers):       # consumed only when B200_DECODE_L2_PREFETCH is set
-            nxt = [layer.self_attn.o_proj.weight]
-            if isinstance(layer.mlp, DecoderMLP):
-                nxt += [layer.mlp.gate_up_proj.weight, layer.mlp.down_proj.weight]
-            else:
-                nxt.append(layer.mlp.gate.weight)
-            if i + 1 < len(self.layers):
-                nxt.append(self.layers[i + 1].self_attn.qkv_proj.weight)
-            layer.self_attn.prefetch_next = nxt
 
     def forward(self, input_ids, positions):
         hidden_states = self.embed_tokens(input_ids)

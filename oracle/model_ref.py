@@ -87,8 +87,9 @@ def param_shapes(cfg: ModelCfg) -> dict[str, tuple[int, ...]]:
     return shapes
 
 
-def seeded_weights(cfg: ModelCfg, seed: int = 0, norm_jitter: float = 0.0) -> dict[str, torch.Tensor]:
-    """Deterministic random-init weights keyed by parameter name: matrices ~ N(0, 0.02),
+def seeded_weights(cfg: ModelCfg, seed: int = 0, norm_jitter: float = 0.0,
+                   std: float = 0.02) -> dict[str, torch.Tensor]:
+    """Deterministic random-init weights keyed by parameter name: matrices ~ N(0, std),
     norm weights 1 (+ jitter * N(0,1) when asked, so the weight multiply is exercised).
     Each tensor draws from its own generator seeded by (seed, sorted position) so the result
     does not depend on which consumer asks first."""
@@ -98,7 +99,7 @@ def seeded_weights(cfg: ModelCfg, seed: int = 0, norm_jitter: float = 0.0) -> di
         if len(shape) == 1:
             w = torch.ones(shape) + norm_jitter * torch.randn(shape, generator=gen)
         else:
-            w = 0.02 * torch.randn(shape, generator=gen)
+            w = std * torch.randn(shape, generator=gen)
         out[name] = w.to(cfg.dtype)
     return out
 
@@ -115,7 +116,8 @@ class StepMeta:
 
 
 def forward(w, cfg: ModelCfg, input_ids, positions, meta: StepMeta, kv_cache, block_size,
-            attn_mode="reference", return_hidden=False, trace: dict | None = None):
+            attn_mode="reference", return_hidden=False, trace: dict | None = None,
+            fp32_logits=False):
     """One model step. kv_cache: [2, L, nb, bs, Hkv, D] (written in place).
     Mirrors Qwen3Model.forward (qwen3.py:175-185) / Qwen3DecoderLayer.forward (:148-161) /
     Qwen3Attention.forward (:74-90) / Qwen3MLP.forward (:115-119) / compute_logits (:216-218)."""
@@ -173,6 +175,8 @@ def forward(w, cfg: ModelCfg, input_ids, positions, meta: StepMeta, kv_cache, bl
     if meta.is_prefill:  # embed_head.py:57-60: logits only for each sequence's last token
         x = x[(meta.cu_seqlens_q[1:] - 1).long()].contiguous()
     head = w["model.embed_tokens.weight"] if cfg.tie_embeddings else w["lm_head.weight"]
+    if fp32_logits:      # the LM-head product before its cast to the model dtype (parity yardstick)
+        return F.linear(x.float(), head.float())
     return F.linear(x, head)
 
 
@@ -227,7 +231,7 @@ class GreedyTrace:
 
 
 def generate_greedy(w, cfg: ModelCfg, prompts, max_tokens, block_size=16, num_blocks=None,
-                    attn_mode="reference", keep_logits=True):
+                    attn_mode="reference", keep_logits=True, fp32_logits=False, force_tokens=None):
     """Greedy (argmax) generation for a fixed batch of prompts, all decoded in lock step;
     blocks are handed out sequentially (sequence i gets a private ascending run).
     Follows the engine loop llm_engine.py:120-176 + model_runner.py:398-452 with the sampler
@@ -249,13 +253,13 @@ def generate_greedy(w, cfg: ModelCfg, prompts, max_tokens, block_size=16, num_bl
         positions, meta = prefill_meta(lens, [t[:(n + block_size - 1) // block_size]
                                               for t, n in zip(tables, lens)], block_size)
         ids = torch.tensor([t for s in seqs for t in s], dtype=torch.int64)
-        logits = forward(w, cfg, ids, positions, meta, kv, block_size, attn_mode)
+        logits = forward(w, cfg, ids, positions, meta, kv, block_size, attn_mode, fp32_logits=fp32_logits)
         for step in range(max_tokens):
             nxt_tok = L.greedy(logits).tolist()
             if keep_logits:
                 trace.logits.append(logits.float().clone())
             for i, t in enumerate(nxt_tok):
-                seqs[i].append(t)
+                seqs[i].append(t if force_tokens is None else force_tokens[step][i])
                 trace.tokens[i].append(t)
             if step == max_tokens - 1:
                 break
@@ -263,5 +267,5 @@ def generate_greedy(w, cfg: ModelCfg, prompts, max_tokens, block_size=16, num_bl
             positions, meta = decode_meta(lens, [t[:(n + block_size - 1) // block_size]
                                                  for t, n in zip(tables, lens)], block_size)
             ids = torch.tensor([s[-1] for s in seqs], dtype=torch.int64)
-            logits = forward(w, cfg, ids, positions, meta, kv, block_size, attn_mode)
+            logits = forward(w, cfg, ids, positions, meta, kv, block_size, attn_mode, fp32_logits=fp32_logits)
     return trace

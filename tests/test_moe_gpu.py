@@ -1,8 +1,6 @@
-"""-m gpu, STAGED (run with B200_RUN_MOE=1, or through tests/test_z_staged_gpu.py with
-B200_RUN_STAGED=1): the sparse-MoE kernels (csrc/moe.cu) and the Qwen3-MoE engine against the
-reference-generated goldens (tests/golden/moe.pt) and the CPU oracle (oracle/moe_ref.py).
-The kernels compile and their index arithmetic is emulated on CPU (tools/emulate_moe_kernels.py);
-they have not run on a B200 yet, which is why the default `pytest -m gpu` run skips this file.
+"""-m gpu: the sparse-MoE kernels (csrc/moe.cu, csrc/moe_umma.cu) and the Qwen3-MoE engine against
+the reference-generated goldens (tests/golden/moe.pt) and the CPU oracle (oracle/moe_ref.py).
+First hardware run: r02, 29 cases green (profiles/r02_validation_summary.log).
 
 Tolerances. Routing: expert ids must equal the reference's wherever the reference's own
 probabilities are not tied at the top-k boundary; weights within one rounding of the model dtype.
@@ -18,9 +16,7 @@ import torch
 
 from oracle import moe_ref
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_RUN_MOE") != "1",
-                                 reason="staged (not yet validated on hardware); set B200_RUN_MOE=1")]
+pytestmark = pytest.mark.gpu
 
 BLOCK_CASES = ("e8_k2", "e32_k4", "e128_k8", "single_token")
 
@@ -206,7 +202,7 @@ def test_tiny_qwen3_moe_cuda_graph_equals_eager():
 
 @pytest.mark.parametrize("big", ["umma", "library"])
 def test_big_gemm_paths_match_the_streaming_kernels(monkeypatch, big):
-    """B200_MOE_BIG_GEMM: prefill-sized batches through the tcgen05 grouped GEMM (csrc/moe_umma.cu) or
+    """ops._MOE_BIG_GEMM: prefill-sized batches through the tcgen05 grouped GEMM (csrc/moe_umma.cu) or
     through torch._grouped_mm must agree with the weight-streaming expert GEMMs -- full and
     expert-parallel plans, row counts that are not multiples of the 128-row tile, an empty expert."""
     from nanovllm import ops
@@ -225,7 +221,7 @@ def test_big_gemm_paths_match_the_streaming_kernels(monkeypatch, big):
         for begin, n in ((0, E), (E // 2, E - E // 2)):
             plan = ops.moe_align(ids, begin, n)
             wa, wb = w13[begin:begin + n].contiguous(), w2[begin:begin + n].contiguous()
-            monkeypatch.setattr(ops, "_MOE_BIG_GEMM", "")
+            monkeypatch.setattr(ops, "_MOE_BIG_GEMM", "stream")
             a = ops.moe_experts(x, wa, wb, ids, w, plan)
             monkeypatch.setattr(ops, "_MOE_BIG_GEMM", big)
             monkeypatch.setattr(ops, "_MOE_BIG_GEMM_ROWS", 1)

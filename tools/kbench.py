@@ -121,6 +121,27 @@ def bench_fa2_prefill(nseq, L, H, G, D):
                 TFLOPs_med=round(flops / med / 1e9, 1), TFLOPs_best=round(flops / best / 1e9, 1))
 
 
+def bench_fa2_prefix_hit(qlen, klen, H, G, D, bs=256):
+    """attention_ori.py:65-66 -- flash_attn_varlen_func with block_table (prefix-cache hit: q shorter
+    than k, K/V from the paged cache); FA2 pages are 256 tokens."""
+    from flash_attn import flash_attn_varlen_func
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nblk = (klen + bs - 1) // bs
+    kc = torch.randn(nblk + 1, bs, G, D, device="cuda", generator=g).to(torch.bfloat16)
+    vc = torch.randn(nblk + 1, bs, G, D, device="cuda", generator=g).to(torch.bfloat16)
+    q = torch.randn(qlen, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    bt = torch.randperm(nblk, device="cuda", generator=g).to(torch.int32).view(1, -1).contiguous()
+    cu_q = torch.tensor([0, qlen], dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor([0, klen], dtype=torch.int32, device="cuda")
+    fn = lambda: flash_attn_varlen_func(q, kc, vc, max_seqlen_q=qlen, cu_seqlens_q=cu_q, max_seqlen_k=klen,
+                                        cu_seqlens_k=cu_k, softmax_scale=D ** -0.5, causal=True,
+                                        block_table=bt)
+    med, best = timeit(fn, iters=10, warmup=3)
+    flops = 4 * H * D * (qlen * (klen - qlen) + qlen * qlen / 2)
+    return dict(kernel="fa2_varlen_prefix_hit", qlen=qlen, klen=klen, H=H, G=G, D=D, bs=bs,
+                ms_med=round(med, 4), TFLOPs_med=round(flops / med / 1e9, 1))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -134,8 +155,11 @@ if __name__ == "__main__":
         res.append(bench_decode(256, 32, 8, 64, 16, 1024))      # Llama-1B
         res.append(bench_decode(1, 16, 8, 128, 16, 8192))
         res.append(bench_decode(16, 16, 8, 128, 16, 1024))
+    if args.what == "prefill16":                 # one shape, few launches: the ncu target
+        res.append(bench_prefill(16, 1024, 16, 8, 128))
     if args.what in ("prefill", "all"):
         res.append(bench_prefill(16, 1024, 16, 8, 128))
+        res.append(bench_prefill(4, 4096, 16, 8, 128))
         res.append(bench_prefill(1, 8192, 32, 8, 64))
         res.append(bench_prefill_prefix_hit(256, 8192, 32, 8, 64, 16))
     if args.what in ("fa2", "all"):
@@ -144,7 +168,9 @@ if __name__ == "__main__":
             res.append(bench_fa2_decode(256, 8, 1, 128, 1024))
             res.append(bench_fa2_decode(256, 32, 8, 64, 1024))
             res.append(bench_fa2_prefill(16, 1024, 16, 8, 128))
+            res.append(bench_fa2_prefill(4, 4096, 16, 8, 128))
             res.append(bench_fa2_prefill(1, 8192, 32, 8, 64))
+            res.append(bench_fa2_prefix_hit(256, 8192, 32, 8, 64))
         except Exception as e:                     # the comparator is optional library code
             res.append(dict(kernel="fa2", unavailable=f"{type(e).__name__}: {e}"[:200]))
     for r in res:

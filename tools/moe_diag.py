@@ -189,7 +189,7 @@ def bench(once=False):
         flops = 2 * T * k * 3 * hidden * inter
         for path in (("stream",) if T <= 512 else ("stream", "umma", "library")):
             prev = (ops._MOE_BIG_GEMM, ops._MOE_BIG_GEMM_ROWS)
-            ops._MOE_BIG_GEMM, ops._MOE_BIG_GEMM_ROWS = ("" if path == "stream" else path), 1
+            ops._MOE_BIG_GEMM, ops._MOE_BIG_GEMM_ROWS = path, 1
             try:
                 us = timeit(lambda: ops.moe_experts(x, w13, w2, ids, w, plan), iters, warm)
                 print(f"{label:22s} {path:8s} {us:9.1f} us  expert-weight stream {wbytes / us / 1e3:8.1f} GB/s  "

@@ -1,0 +1,37 @@
+#!/usr/bin/env bash
+# Round-2 evidence run on ONE GPU: the full -m gpu suite (with the parity figures printed), the
+# kernel table against FA2, ncu captures of the prefill kernels, compute-sanitizer logs.
+#   gpurun --timeout 2400 -- 'bash tools/profile_r02.sh [tests|kbench|ncu|sanitize ...]'
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+what=${*:-tests kbench ncu sanitize}
+for w in $what; do
+case $w in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -q -s -rs > gpurun_out/r02_gpu_tests.log 2>&1
+  echo "tests rc=$? $(tail -n 1 gpurun_out/r02_gpu_tests.log)"
+  grep -E "vs oracle|vs reference" gpurun_out/r02_gpu_tests.log > gpurun_out/r02_parity_measured.log
+  cat gpurun_out/r02_parity_measured.log ;;
+kbench)
+  timeout 600 python tools/kbench.py all > gpurun_out/r02_kbench.jsonl 2> gpurun_out/r02_kbench.err
+  echo "kbench rc=$?"
+  B200_PREFILL_KERNEL=umma2 timeout 300 python tools/kbench.py prefill > gpurun_out/r02_kbench_umma2.jsonl 2>&1
+  cat gpurun_out/r02_kbench_umma2.jsonl ;;
+ncu)
+  for k in umma umma2; do
+    B200_PREFILL_KERNEL=$k timeout 600 ncu --set full --clock-control none --import-source on \
+      -k regex:prefill_umma -s 4 -c 1 -f -o gpurun_out/r02_prefill_$k python tools/kbench.py prefill16 \
+      > gpurun_out/r02_ncu_$k.log 2>&1
+    echo "ncu $k rc=$?"
+  done ;;
+sanitize)
+  for tool in memcheck racecheck; do
+    timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 \
+      python -m pytest tests/test_kernels_gpu.py -q -x \
+      -k "decode_ragged or decode_golden or prefill_golden or prefill_ragged or kv_scatter_golden or prefill_paged or qknorm_rope_cache or layers_golden" \
+      > gpurun_out/r02_sanitizer_$tool.log 2>&1
+    echo "sanitizer $tool rc=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/r02_sanitizer_$tool.log | tail -n 2 | tr '\n' ' ')"
+  done ;;
+esac
+done

@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--ctx", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--tp", action="store_true")
+    ap.add_argument("--shard-of", type=int, default=0,
+                    help="single process: rank 0's shard of an N-way tensor-parallel model, collectives "
+                         "skipped (Config.tp_shard_emulation) -- the per-rank compute of a TP=N step")
     ap.add_argument("--mem-util", type=float, default=0.7)
     ap.add_argument("--kv-cache-dtype", default="auto")
     ap.add_argument("--out", default=None, help="also write the table to this file (rank 0)")
@@ -48,7 +51,8 @@ def main():
     llm = LLM(args.model, kvcache_block_size=16, max_num_seqs=args.batch, max_model_len=4096,
               max_num_batched_tokens=16384, tensor_parallel_size=world if args.tp else 1,
               distributed_launch="env", gpu_memory_utilization=args.mem_util,
-              kv_cache_dtype=args.kv_cache_dtype, seed=0)
+              kv_cache_dtype=args.kv_cache_dtype, seed=0, tp_shard_emulation=args.shard_of,
+              graph_batch_sizes=(args.batch,))
     rnd = random.Random(0)
     sp = SamplingParams(temperature=0.6, ignore_eos=True, max_tokens=args.steps + 64)
     for _ in range(args.batch):
@@ -87,7 +91,7 @@ def main():
             print(f"event walk failed ({type(e).__name__}: {e}); key_averages() instead")
             print(prof.key_averages().table(row_limit=40))
             agg, busy = collections.OrderedDict(), 1.0
-        lines = [f"model={args.model} tp={world if args.tp else 1} batch={args.batch} ctx~{args.ctx} "
+        lines = [f"model={args.model} tp={world if args.tp else 1} shard_of={args.shard_of} batch={args.batch} ctx~{args.ctx} "
                  f"step (no profiler) = {plain_ms:.3f} ms; GPU-busy under profiler = "
                  f"{busy / args.steps / 1e3:.3f} ms/step over {args.steps} steps",
                  f"{'launches/step':>13} {'avg us':>9} {'us/step':>10} {'share':>7}  kernel"]
