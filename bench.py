@@ -113,6 +113,79 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured burst cuBLAS bf16 (MEASURED_PEAKS.json)"
+    return 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def prefill_roofline():
+    """The tensor-bound kernel of the path (prefill_umma_kernel) timed alone with CUDA events on the
+    shapes BASELINE names: configs[1]'s prefill batch (16 x 1024 tokens, Qwen3-0.6B heads) and configs[2]
+    (Llama-3.2-1B, 8192-token prompt: whole, and the prefix-cache-hit form -- 256 new tokens against
+    7936 cached ones read through block tables). Flops = 4 * H * D * sum over rows of visible keys
+    (causal); inputs rotate over copies totalling > L2."""
+    from nanovllm import ops
+    peak, src = tensor_peak()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    bf = torch.bfloat16
+
+    def timed(fns, iters=24):
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fns[i % len(fns)]()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / iters
+
+    def packed(nseq, L, H, G, D, copies):
+        T = nseq * L
+        cu = torch.arange(0, T + 1, L, dtype=torch.int32, device="cuda")
+        out = torch.empty(T, H * D, dtype=bf, device="cuda")
+        fns = []
+        for _ in range(copies):
+            qkv = torch.randn(T, (H + 2 * G) * D, device="cuda", generator=g).to(bf)
+            q = qkv[:, :H * D].unflatten(1, (H, D))
+            k = qkv[:, H * D:(H + G) * D].unflatten(1, (G, D))
+            v = qkv[:, (H + G) * D:].unflatten(1, (G, D))
+            fns.append(lambda q=q, k=k, v=v: ops.prefill_varlen_attn(q, k, v, cu, cu, L, L, D ** -0.5, G, out=out))
+        sec = timed(fns)
+        flops = 2 * L * L * H * D * nseq
+        return {"shape": f"{nseq} x {L} tokens, H={H} Hkv={G} D={D}, packed, causal", "us": sec * 1e6,
+                "tflops": flops / sec / 1e12, "frac": flops / sec / 1e12 / peak}
+
+    def prefix_hit(qlen, klen, H, G, D, bs, copies):
+        nblk = (klen + bs - 1) // bs
+        cu_q = torch.tensor([0, qlen], dtype=torch.int32, device="cuda")
+        cu_k = torch.tensor([0, klen], dtype=torch.int32, device="cuda")
+        out = torch.empty(qlen, H * D, dtype=bf, device="cuda")
+        q = torch.randn(qlen, H, D, device="cuda", generator=g).to(bf)
+        fns = []
+        for _ in range(copies):
+            kc = torch.randn(nblk + 1, bs, G * D, device="cuda", generator=g).to(bf)
+            vc = torch.randn(nblk + 1, bs, G * D, device="cuda", generator=g).to(bf)
+            bt = torch.randperm(nblk, device="cuda", generator=g).to(torch.int32).view(1, -1).contiguous()
+            fns.append(lambda kc=kc, vc=vc, bt=bt: ops.prefill_varlen_attn(
+                q, kc, vc, cu_q, cu_k, qlen, klen, D ** -0.5, G, block_tables=bt, out=out))
+        sec = timed(fns)
+        flops = 4 * H * D * (qlen * (klen - qlen) + qlen * qlen / 2)
+        return {"shape": f"q {qlen} / k {klen} tokens, H={H} Hkv={G} D={D}, paged block {bs} (prefix-cache hit)",
+                "us": sec * 1e6, "tflops": flops / sec / 1e12, "frac": flops / sec / 1e12 / peak}
+
+    main = packed(16, 1024, 16, 8, 128, 2)
+    shapes = [main, packed(4, 4096, 16, 8, 128, 2), packed(1, 8192, 32, 8, 64, 4),
+              prefix_hit(256, 8192, 32, 8, 64, 16, 16)]
+    return {"bound": "tensor", "kernel": "prefill_umma_kernel", "achieved": main["tflops"], "peak": peak,
+            "unit": "TFLOP/s", "frac": main["frac"], "peak_source": src, "traffic": None,
+            "shapes": shapes}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed regions."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -531,6 +604,8 @@ def main():
     del runner
     release(llm)
     dbg(rank, 'after exit')
+    if world == 1 and args.model == "qwen3-0.6b":
+        line["prefill_roofline"] = prefill_roofline()
     if world > 1 and not args.tp and not args.no_tp_block:
         # the replicas above say nothing about the collective design: the same run also measures the
         # tensor-parallel path (BASELINE configs[3]) over all `world` GPUs, with its TP=1 comparison

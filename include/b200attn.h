@@ -152,6 +152,11 @@ int b200_paged_decode_attn_fp8(void* out, const void* q, const void* k_cache, co
  *   keys are its first (cu_seqlens_k[i+1]-cu_seqlens_k[i]) cached tokens via block_tables[i].
  * total_q / total_k: number of packed rows in q / in k,v (= cu_seqlens[num_seqs]; bounds of the
  * TMA tensor maps; total_k is ignored in paged mode).
+ * workspace (optional, 16-byte aligned device memory owned by the caller, may be NULL): when the
+ *   (sequence, head, 256-row) grid would leave most SMs idle -- the prefix-cache-hit form, a few
+ *   hundred query rows against thousands of cached keys -- up to 8 CTAs split one row block along
+ *   the keys, write un-normalised fp32 partials here and a second small kernel merges them. Needs
+ *   total_q * num_heads * splits * (head_dim + 2) * 4 bytes; see b200_prefill_workspace_size.
  * Causal mask is bottom-right aligned (query row r of a sequence with Lq queries and Lk keys
  * sees keys 0 .. r + Lk - Lq), == NPU sparse_mode=3 and flash-attn causal; identical to the
  * oracle's top-left mask whenever Lq == Lk, which is the only case the reference runner
@@ -166,7 +171,12 @@ int b200_prefill_varlen_attn(void* out, const void* q, const void* k, const void
                              int64_t out_stride, const int32_t* block_tables,
                              int32_t block_table_stride, int32_t num_blocks,
                              int32_t block_size, float scale, int32_t dtype,
-                             b200_stream_t stream);
+                             void* workspace, int64_t workspace_bytes, b200_stream_t stream);
+
+/* Bytes of split-KV workspace that let b200_prefill_varlen_attn use every SM for ANY launch it would
+ * split (few query rows against many keys): the largest such launch has 148 CTAs x 256 rows of
+ * un-normalised fp32 partials. A smaller (or NULL) workspace is legal: fewer (or no) key splits. */
+int64_t b200_prefill_workspace_size(int32_t head_dim);
 
 /* ---------------------------------------------------------------------------------
  * K8  fused qkv epilogue: split -> per-head RMSNorm(q,k) -> NeoX RoPE(q,k) -> KV scatter.

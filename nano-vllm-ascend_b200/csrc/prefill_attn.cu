@@ -247,22 +247,13 @@ int prefill_umma_launch(void* out, const void* q, const void* k, const void* v, 
                         int max_seqlen_q, int H, int Hkv, int D, int64_t q_stride, int64_t k_stride,
                         int64_t v_stride, int64_t out_stride, const int32_t* block_tables,
                         int bt_stride, int num_blocks, int block_size, float scale, int dtype,
+                        void* workspace, int64_t workspace_bytes, int max_seqlen_k,
                         cudaStream_t stream);  // prefill_umma.cu
-int prefill_umma2_launch(void* out, const void* q, const void* k, const void* v, const int32_t* cu_q,
-                         const int32_t* cu_k, int num_seqs, int total_q, int total_k,
-                         int max_seqlen_q, int H, int Hkv, int D, int64_t q_stride, int64_t k_stride,
-                         int64_t v_stride, int64_t out_stride, const int32_t* block_tables,
-                         int bt_stride, int num_blocks, int block_size, float scale, int dtype,
-                         cudaStream_t stream);  // prefill_umma2.cu (opt-in)
-
-// B200_PREFILL_KERNEL: unset / "umma" = prefill_umma.cu (default), "umma2" = prefill_umma2.cu
-// (opt-in until validated on hardware), "mma_sync" = the kernel in this file. Returns 1, 2, 0.
+// B200_PREFILL_KERNEL=mma_sync forces the kernel in this file (A/B checks); default = prefill_umma.cu.
 static int prefill_kernel_choice() {
   static int v = [] {
     const char* e = getenv("B200_PREFILL_KERNEL");
-    if (e != nullptr && strcmp(e, "mma_sync") == 0) return 0;
-    if (e != nullptr && strcmp(e, "umma2") == 0) return 2;
-    return 1;
+    return (e != nullptr && strcmp(e, "mma_sync") == 0) ? 0 : 1;
   }();
   return v;
 }
@@ -270,6 +261,11 @@ static int prefill_kernel_choice() {
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int64_t b200_prefill_workspace_size(int32_t head_dim) {
+  // 148 CTAs x 256 rows x (head_dim fp32 of O + m + l): the most a split launch can write
+  return (int64_t)148 * 256 * (head_dim + 2) * 4;
+}
 
 extern "C" int b200_prefill_varlen_attn(void* out, const void* q, const void* k, const void* v,
                                         const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
@@ -280,7 +276,8 @@ extern "C" int b200_prefill_varlen_attn(void* out, const void* q, const void* k,
                                         int64_t k_stride, int64_t v_stride, int64_t out_stride,
                                         const int32_t* block_tables, int32_t block_table_stride,
                                         int32_t num_blocks, int32_t block_size, float scale,
-                                        int32_t dtype, b200_stream_t stream) {
+                                        int32_t dtype, void* workspace, int64_t workspace_bytes,
+                                        b200_stream_t stream) {
   B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
   B200_RETURN_IF(num_seqs < 0 || max_seqlen_q < 0 || max_seqlen_k < 0 || num_heads <= 0 ||
                      num_kv_heads <= 0,
@@ -306,9 +303,10 @@ extern "C" int b200_prefill_varlen_attn(void* out, const void* q, const void* k,
   cudaStream_t s = (cudaStream_t)stream;
   const int choice = prefill_kernel_choice();
   if (choice != 0) {
-    const int rc = (choice == 2 ? prefill_umma2_launch : prefill_umma_launch)(out, q, k, v, cu_seqlens_q, cu_seqlens_k, num_seqs, total_q,
+    const int rc = prefill_umma_launch(out, q, k, v, cu_seqlens_q, cu_seqlens_k, num_seqs, total_q,
         total_k, max_seqlen_q, num_heads, num_kv_heads, head_dim, q_stride, k_stride, v_stride,
-        out_stride, block_tables, block_table_stride, num_blocks, block_size, scale, dtype, s);
+        out_stride, block_tables, block_table_stride, num_blocks, block_size, scale, dtype,
+        workspace, workspace_bytes, max_seqlen_k, s);
     if (rc != B200_ERR_UNSUPPORTED) return rc;
   }
   PrefillParams p;

@@ -45,7 +45,8 @@ PROTOTYPES = {
                                            c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                            c_int32, c_int32, c_int32, c_float, c_int32,
-                                           c_void_p]),
+                                           c_void_p, c_int64, c_void_p]),
+    "b200_prefill_workspace_size": (c_int64, [c_int32]),
     "b200_qknorm_rope_cache": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_float, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                          c_int32, c_int32, c_int32, c_int64, c_int32, c_int32,

@@ -8,11 +8,15 @@ copies) for small messages, two-shot (b200_allreduce_add_rmsnorm_twoshot, each r
 of the rows and pushes the sums into every rank's gather buffer) for larger ones. Set-up uses
 torch.distributed only to exchange the 64-byte IPC handles.
 
-With ``B200_NVLS_ALLREDUCE=1`` the region is instead a torch symmetric-memory allocation (plumbing:
-cuMemCreate + handle exchange + cuMulticastBindMem done by ``torch.distributed._symmetric_memory``),
-which yields the same per-rank peer pointers PLUS one multicast address for the whole region; larger
-messages then go through b200_allreduce_add_rmsnorm_nvls (in-switch reduce + in-switch broadcast).
-Staged: compiled, not yet run on hardware.
+Form selection (``mode``): one-shot while (world-1) x message <= 4 MB, two-shot beyond (both validated on
+hardware inside the engine, eager and CUDA-graph decode, r02), NCCL for shapes neither takes.
+``B200_ALLREDUCE`` forces one form for every shape it can take -- a measurement aid for A/B runs:
+``nccl`` | ``oneshot`` | ``twoshot`` | ``nvls`` | ``nvls_fused``. The two NVLS values make the region a
+torch symmetric-memory allocation (plumbing: cuMemCreate + handle exchange + cuMulticastBindMem done by
+``torch.distributed._symmetric_memory``), which yields the same per-rank peer pointers PLUS one multicast
+address for the whole region; messages then go through b200_allreduce_add_rmsnorm_nvls[_fused]
+(in-switch reduce + in-switch broadcast). NVLS status (r02): the kernels pass their 2-GPU tests and the
+eager TP=2 engine test; the CUDA-graph TP=2 engine test timed out, so it is never selected by default.
 """
 from __future__ import annotations
 
@@ -45,8 +49,10 @@ class PeerAllReduce:
         total = 3 * self.max_bytes + 2 * self.FLAG_BYTES
         self.multicast_ptr = 0       # multicast address of the region (NVLS), 0 = not available
         self._symm = None
-        nvls = os.environ.get("B200_NVLS_ALLREDUCE", "0")
-        if nvls != "0":
+        self.forced = os.environ.get("B200_ALLREDUCE", "auto").lower()
+        if self.forced not in ("auto", "nccl", "oneshot", "twoshot", "nvls", "nvls_fused"):
+            raise ValueError(f"B200_ALLREDUCE={self.forced!r}: expected auto|nccl|oneshot|twoshot|nvls|nvls_fused")
+        if self.forced in ("nvls", "nvls_fused"):
             self._map_symmetric(total)
         else:
             self._map_ipc(total)
@@ -55,12 +61,6 @@ class PeerAllReduce:
         self._gather = arr(*[p + 2 * self.max_bytes for p in self.peer_ptrs])
         self._flags = arr(*[p + 3 * self.max_bytes for p in self.peer_ptrs])
         self._state = self.local_ptr + 3 * self.max_bytes + self.FLAG_BYTES
-        # two-shot kernel: compiled and unit-tested on 2 GPUs only when enabled; opt-in until the
-        # multi-GPU validation recorded in DESIGN.md section 6 is done
-        self.two_shot = os.environ.get("B200_TWOSHOT_ALLREDUCE", "0") == "1"
-        self.nvls_all = nvls in ("all", "fused-all")   # tuning aid: multicast form for every message size
-        # "fused" / "fused-all": the one-pass form with a row-sliced residual (see allreduce.cu)
-        self.nvls_fused = nvls in ("fused", "fused-all")
         self._parity = 0
         self.pending = None          # (tensor, parity) written by the last deferred row-parallel GEMM
         dist.barrier()
@@ -98,26 +98,28 @@ class PeerAllReduce:
             raise RuntimeError("symmetric memory: local buffer pointer mismatch")
         self.multicast_ptr = int(self._symm.multicast_ptr or 0)
         if not self.multicast_ptr:
-            raise RuntimeError("B200_NVLS_ALLREDUCE is set but this platform offers no multicast "
+            raise RuntimeError("B200_ALLREDUCE asks for NVLS but this platform offers no multicast "
                                "(NVSwitch / driver support missing)")
 
     # one-shot: every rank pulls (world-1) full copies over NVLink; beyond a few MB of incoming
-    # traffic a bandwidth-optimal algorithm (NCCL; later a row-sliced two-shot kernel) wins.
-    # Measured: Qwen3-0.6B TP=2 (0.5 MB in) +9 % step throughput over NCCL; Qwen3-32B TP=8
-    # (18 MB in per call) is bandwidth-bound at ~26 us per call.
+    # traffic the row-sliced two-shot kernel (reduce a slice, push the sums) moves 2(world-1)/world of a
+    # message instead. Measured: Qwen3-0.6B TP=2 (0.5 MB in) +9 % step throughput over NCCL;
+    # Qwen3-32B TP=8 (18 MB in per call) one-shot is bandwidth-bound at ~26 us per call.
     ONE_SHOT_MAX_INCOMING = 4 << 20
 
     def mode(self, rows: int, hidden: int, itemsize: int) -> str | None:
-        """"one" / "two" (shot) when the fused kernel takes this message, None for NCCL."""
+        """"one" / "two" / "nvls" / "nvls_fused" when a fused kernel takes this message, None for NCCL."""
         nbytes = rows * hidden * itemsize
-        if nbytes > self.max_bytes or hidden % 8 != 0 or hidden > 8192:
+        if self.forced == "nccl" or nbytes > self.max_bytes or hidden % 8 != 0 or hidden > 8192:
             return None
-        if self.multicast_ptr and rows >= self.world and (
-                self.nvls_all or (self.world - 1) * nbytes > self.ONE_SHOT_MAX_INCOMING):
-            return "nvls_fused" if self.nvls_fused else "nvls"
-        if (self.world - 1) * nbytes <= self.ONE_SHOT_MAX_INCOMING:
+        sliced_ok = rows >= self.world           # the row-sliced forms need a row per rank
+        if self.forced in ("nvls", "nvls_fused"):
+            return self.forced if sliced_ok else "one"
+        if self.forced == "twoshot":
+            return "two" if sliced_ok else "one"
+        if self.forced == "oneshot" or (self.world - 1) * nbytes <= self.ONE_SHOT_MAX_INCOMING:
             return "one"
-        return "two" if self.two_shot and rows >= self.world else None
+        return "two" if sliced_ok else None
 
     def fits(self, rows: int, hidden: int, itemsize: int) -> bool:
         return self.mode(rows, hidden, itemsize) is not None

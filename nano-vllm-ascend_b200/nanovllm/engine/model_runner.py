@@ -101,15 +101,17 @@ class ModelRunner:
         self.model.eval()
         self.spec = self.model.spec
         self.comm = None
-        if self.world_size > 1 and os.environ.get("B200_PEER_ALLREDUCE", "1") != "0":
+        if self.world_size > 1:
             from ..comm import PeerAllReduce, set_comm
             self.comm = PeerAllReduce(self.device)
             set_comm(self.comm)
         self.sampler = Sampler(seed=config.seed)
-        # Opt-in until validated on hardware: sample on every rank over its own vocabulary shard and
-        # MAX-all-reduce 8 bytes per row, instead of gathering [B, vocab] logits on rank 0, sampling
-        # there and broadcasting the ids (reference: embed_head.py:62-65 + sampler.py on rank 0).
-        self.sharded_sampling = self.world_size > 1 and os.environ.get("B200_SHARDED_SAMPLING", "0") == "1"
+        # Tensor parallelism: sample on every rank over its own vocabulary shard and MAX-all-reduce 8
+        # bytes per row, instead of gathering [B, vocab] logits on rank 0, sampling there and
+        # broadcasting the ids (reference: embed_head.py:62-65 + sampler.py on rank 0). Bit-identical
+        # ids (tests/test_kernels_gpu.py, tests/test_tp_gpu.py); B200_SHARDED_SAMPLING=0 restores the
+        # gather for A/B timing.
+        self.sharded_sampling = self.world_size > 1 and os.environ.get("B200_SHARDED_SAMPLING", "1") != "0"
 
         self._warmup_prefill()
         self._allocate_kv_cache()

@@ -174,10 +174,25 @@ def paged_decode_attn_fp8(q, k_cache, v_cache, block_tables, context_lens, scale
     return out
 
 
+_prefill_ws: dict = {}
+
+
+def prefill_workspace(device, head_dim: int) -> torch.Tensor:
+    """The split-KV workspace of the prefill kernel (b200_prefill_workspace_size bytes, a few MB),
+    one per device, allocated on first use -- outside CUDA-graph capture; prefill runs eagerly."""
+    key = (device, head_dim)
+    ws = _prefill_ws.get(key)
+    if ws is None:
+        n = int(_C.load().b200_prefill_workspace_size(int(head_dim)))
+        ws = _prefill_ws[key] = torch.empty(n, dtype=torch.uint8, device=device)
+    return ws
+
+
 def prefill_varlen_attn(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, scale,
-                        num_kv_heads, block_tables=None, out=None):
+                        num_kv_heads, block_tables=None, out=None, workspace="auto"):
     """K4/K5. q [Tq, H, D]; packed mode: k/v [Tk, Hkv, D]; paged mode (block_tables given):
-    k/v are the caches [nb, bs, Hkv*D]. Returns out [Tq, H*D]."""
+    k/v are the caches [nb, bs, Hkv*D]. Returns out [Tq, H*D]. workspace: "auto" (the per-device
+    split-KV workspace), None (never split the keys across CTAs) or a uint8 CUDA tensor."""
     _need_cuda(q, k, v, cu_seqlens_q, cu_seqlens_k, block_tables)
     Tq, H, D = q.shape
     if q.stride(2) != 1 or q.stride(1) != D:
@@ -200,12 +215,15 @@ def prefill_varlen_attn(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_s
         ks = k.stride(0) if k.shape[0] > 1 else num_kv_heads * D
         vs = v.stride(0) if v.shape[0] > 1 else num_kv_heads * D
         bt_ptr, bt_stride = None, 0
+    if isinstance(workspace, str):
+        workspace = prefill_workspace(q.device, D)
+    ws_ptr, ws_bytes = (None, 0) if workspace is None else (workspace.data_ptr(), workspace.numel())
     _C.check(_C.load().b200_prefill_varlen_attn(
         out.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), cu_seqlens_q.data_ptr(),
         cu_seqlens_k.data_ptr(), num_seqs, Tq, 0 if block_tables is not None else k.shape[0],
         int(max_seqlen_q), int(max_seqlen_k), H, num_kv_heads,
         D, q.stride(0) if Tq > 1 else H * D, ks, vs, out.stride(0) if Tq > 1 else H * D, bt_ptr,
-        bt_stride, nb, bs, float(scale), _dt(q), _stream()), "b200_prefill_varlen_attn")
+        bt_stride, nb, bs, float(scale), _dt(q), ws_ptr, ws_bytes, _stream()), "b200_prefill_varlen_attn")
     return out
 
 

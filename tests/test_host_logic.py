@@ -120,19 +120,6 @@ def test_fp8_oracle_and_fragment_map():
             E.run(D, h, G=8, valid=5, seed=2)
 
 
-def test_prefill_umma2_barrier_protocol_simulation():
-    """Randomised simulation of the mbarrier / TMEM hand-offs of prefill_umma2_kernel (producers, MMA
-    issuer, in-order tensor pipe, softmax threads): every resource holds what its consumer expects
-    and every run terminates, for all (n_tiles[0], n_tiles[1]) shapes the kernel can see."""
-    import random
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import simulate_umma2_protocol as P
-    for n0, n1 in [(1, 0), (1, 1), (1, 2), (2, 3), (3, 3), (5, 6), (6, 0)]:
-        for seed in range(6):
-            P.Sim((n0, n1), random.Random(seed * 31 + n0 * 7 + n1)).run()
-
-
-# ------------------------------------------------------------------ front-end contract
 def test_sampling_params_and_config():
     from nanovllm import SamplingParams
     from nanovllm.config import Config
@@ -614,21 +601,21 @@ def test_fused_allreduce_form_selection():
     """comm.PeerAllReduce.mode(): which fused all-reduce form serves a message (pure host logic)."""
     from nanovllm.comm import PeerAllReduce
     c = object.__new__(PeerAllReduce)
-    c.world, c.max_bytes, c.two_shot, c.multicast_ptr, c.nvls_all, c.nvls_fused = 8, 4 << 20, False, 0, False, False
+    c.world, c.max_bytes, c.multicast_ptr, c.forced = 8, 4 << 20, 0, "auto"
     assert c.mode(256, 1024, 2) == "one"            # Qwen3-0.6B TP=8: 7 x 512 KiB incoming
-    assert c.mode(256, 5120, 2) is None             # Qwen3-32B TP=8: 18 MB incoming -> NCCL by default
-    assert c.mode(4096, 5120, 2) is None            # prefill-sized: beyond the buffer
+    assert c.mode(256, 5120, 2) == "two"            # Qwen3-32B TP=8: 18 MB incoming -> row-sliced two-shot
+    assert c.mode(4, 5120 * 8, 2) is None           # hidden beyond the kernels' row width
+    assert c.mode(4096, 5120, 2) is None            # prefill-sized: beyond the buffer -> NCCL
     assert c.mode(256, 1030, 2) is None             # hidden % 8
-    c.two_shot = True
-    assert c.mode(256, 5120, 2) == "two" and c.mode(4, 5120 * 8, 2) is None
-    c.multicast_ptr = 0x7f0000000000                # NVLS region mapped
-    assert c.mode(256, 5120, 2) == "nvls"
-    assert c.mode(256, 1024, 2) == "one"            # small messages stay one-shot (one barrier)
-    assert c.mode(4, 8192, 2) == "one"              # fewer rows than ranks: never nvls
-    c.nvls_all = True
-    assert c.mode(256, 1024, 2) == "nvls" and c.mode(4, 8192, 2) == "one"
-    c.nvls_fused = True
-    assert c.mode(256, 5120, 2) == "nvls_fused" and c.mode(4, 8192, 2) == "one"
+    c.world = 2
+    assert c.mode(256, 5120, 2) == "one"            # TP=2: 2.6 MB incoming
+    c.world = 8
+    for forced, big, small, few_rows in (("nccl", None, None, None), ("oneshot", "one", "one", "one"),
+                                         ("twoshot", "two", "two", "one"), ("nvls", "nvls", "nvls", "one"),
+                                         ("nvls_fused", "nvls_fused", "nvls_fused", "one")):
+        c.forced = forced
+        assert (c.mode(256, 5120, 2), c.mode(256, 1024, 2), c.mode(4, 8192, 2)) == (big, small, few_rows), forced
+        assert c.mode(4096, 5120, 2) is None        # a forced form never takes what does not fit the region
 
 
 def _ep_worker(rank, world, port, out_q):

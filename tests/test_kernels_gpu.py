@@ -383,6 +383,40 @@ def test_prefill_paged_prefix_hit(bs):
     assert (o.float() - want).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("H,G,D,bs,qlens,klens", [
+    (32, 8, 64, 16, [256], [8192]),                     # BASELINE config 3: Llama-3.2-1B, 7936-token prefix hit
+    (16, 8, 128, 16, [200, 33], [4096, 150]),           # one sequence with fewer key tiles than splits
+    (8, 1, 128, 256, [256, 256], [2048, 1999]),         # 32B TP=8 shard shape, reference page size
+])
+def test_prefill_split_kv(H, G, D, bs, qlens, klens):
+    """Few query rows against many cached keys: the launch splits every (sequence, head, 256 rows)
+    along the keys over several CTAs (un-normalised partials in the workspace + merge kernel). Against
+    the oracle's fp32 evaluation, and against the same launch with the split disabled."""
+    ops = _ops()
+    n = len(qlens)
+    _, kc, vc, _, bt = _decode_case(n, H, G, D, bs, klens, seed=H + D)
+    g = torch.Generator().manual_seed(4)
+    cu_q = torch.tensor([0] + list(torch.tensor(qlens).cumsum(0)), dtype=torch.int32)
+    q = torch.randn(int(cu_q[-1]), H, D, generator=g).to(BF)
+    kp, vp, cu_k = A.gather_paged_kv(kc, vc, bt, klens)
+    want = A.prefill_attention(q, kp, vp, cu_q, cu_k, G, D, mode="exact", scale=D ** -0.5,
+                               causal_align="bottom_right")
+    nb = kc.shape[0]
+    args = (q.cuda(), kc.cuda().view(nb, bs, G * D), vc.cuda().view(nb, bs, G * D), cu_q.cuda(), cu_k.cuda(),
+            max(qlens), max(klens), D ** -0.5, G)
+    before = ops.launch_count()
+    split = ops.prefill_varlen_attn(*args, block_tables=bt.cuda()).cpu()
+    assert ops.launch_count() - before == 2, "expected the split launch (attention + merge kernel)"
+    whole = ops.prefill_varlen_attn(*args, block_tables=bt.cuda(), workspace=None).cpu()
+    assert (split.float() - want).abs().max() < 2e-2
+    assert (whole.float() - want).abs().max() < 2e-2
+    assert (split.float() - whole.float()).abs().max() < 1.6e-2     # both round the same fp32 value to bf16
+    # packed K/V take the same path
+    packed = ops.prefill_varlen_attn(q.cuda(), kp.cuda(), vp.cuda(), cu_q.cuda(), cu_k.cuda(), max(qlens),
+                                     max(klens), D ** -0.5, G).cpu()
+    assert (packed.float() - want).abs().max() < 2e-2
+
+
 # ------------------------------------------------------------------ sampling tail
 def test_sample_argmax_and_gumbel():
     ops = _ops()

@@ -1,5 +1,6 @@
-"""-m gpu, needs >= 2 GPUs: tensor-parallel engine (NCCL all-reduce in the row-parallel linears,
-vocab-parallel embedding / LM head gather, sampled ids broadcast) against the single-GPU engine."""
+"""-m gpu, needs >= 2 GPUs: tensor-parallel engine (fused NVLink all-reduce + add + RMSNorm after the
+row-parallel linears, vocab-parallel embedding, vocab-sharded sampling) against the single-GPU engine,
+and the fused all-reduce kernels against all-reduce + the reference's add_rms_forward."""
 import os
 import random
 
@@ -14,24 +15,39 @@ def _need_gpus(n):
         pytest.skip(f"needs {n} GPUs, have {torch.cuda.device_count()}")
 
 
-def _run(tp, prompts, enforce_eager, port):
+def _run(tp, prompts, enforce_eager, port, allreduce="auto", sharded_sampling="1"):
     from nanovllm import LLM, SamplingParams
-    llm = LLM("tiny-qwen3", seed=3, norm_jitter=0.1, kvcache_block_size=16, max_num_seqs=8,
-              max_model_len=256, max_num_batched_tokens=1024, num_kvcache_blocks=128,
-              tensor_parallel_size=tp, enforce_eager=enforce_eager, hccl_port=port)
-    outs = llm.generate(prompts, SamplingParams(temperature=1.0, max_tokens=24, ignore_eos=True,
-                                                greedy=True), use_tqdm=False)
-    llm.exit()
+    # read by comm.PeerAllReduce / ModelRunner at construction, in this process and in the spawned workers
+    saved = {k: os.environ.get(k) for k in ("B200_ALLREDUCE", "B200_SHARDED_SAMPLING")}
+    os.environ["B200_ALLREDUCE"] = allreduce
+    os.environ["B200_SHARDED_SAMPLING"] = sharded_sampling
+    try:
+        llm = LLM("tiny-qwen3", seed=3, norm_jitter=0.1, kvcache_block_size=16, max_num_seqs=8,
+                  max_model_len=256, max_num_batched_tokens=1024, num_kvcache_blocks=128,
+                  tensor_parallel_size=tp, enforce_eager=enforce_eager, hccl_port=port)
+        outs = llm.generate(prompts, SamplingParams(temperature=1.0, max_tokens=24, ignore_eos=True,
+                                                    greedy=True), use_tqdm=False)
+        llm.exit()
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
     return [o["token_ids"] for o in outs]
 
 
+_PORTS = iter(range(28101, 28400, 2))
+
+
 @pytest.mark.parametrize("enforce_eager", [True, False])
-def test_tp2_matches_tp1(enforce_eager):
+@pytest.mark.parametrize("allreduce,sharded_sampling", [("auto", "1"), ("twoshot", "1"), ("nccl", "0")])
+def test_tp2_matches_tp1(enforce_eager, allreduce, sharded_sampling):
+    """TP=2 engine == TP=1 token ids with the default collectives (one-shot fused all-reduce at this
+    size, vocab-sharded sampling), with every all-reduce forced through the two-shot kernel, and with
+    plain NCCL + logits gather (the reference's structure)."""
     _need_gpus(2)
     rnd = random.Random(8)
     prompts = [[rnd.randint(0, 511) for _ in range(n)] for n in (9, 40, 17)]
-    want = _run(1, prompts, True, 28011)
-    got = _run(2, prompts, enforce_eager, 28013 if enforce_eager else 28015)
+    want = _run(1, prompts, True, next(_PORTS))
+    got = _run(2, prompts, enforce_eager, next(_PORTS), allreduce, sharded_sampling)
     # the sharded sums are reassociated (two partial products + all-reduce), so a token may only
     # differ where the logits nearly tie; the tiny model's margins are >= 0.1, far above that
     assert got == want
@@ -130,11 +146,10 @@ def test_fused_peer_allreduce_twoshot_kernel():
     assert _run_ar_workers(2, 28033, _TWO_SHOT_CASES) == {0: True, 1: True}
 
 
-@pytest.mark.skipif(os.environ.get("B200_NVLS_ALLREDUCE", "0") == "0",
-                    reason="staged: needs B200_NVLS_ALLREDUCE=1 (symmetric-memory region + multicast)")
-def test_fused_peer_allreduce_nvls_kernel():
+def test_fused_peer_allreduce_nvls_kernel(monkeypatch):
     """b200_allreduce_add_rmsnorm_nvls (multimem.ld_reduce / multimem.st through the NVSwitch
     multicast mapping torch symmetric memory sets up)."""
     _need_gpus(2)
+    monkeypatch.setenv("B200_ALLREDUCE", "nvls")      # symmetric-memory region (inherited by the workers)
     assert _run_ar_workers(2, 28035, _NVLS_CASES) == {0: True, 1: True}
     assert _run_ar_workers(2, 28037, _NVLS_FUSED_CASES) == {0: True, 1: True}

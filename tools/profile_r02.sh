@@ -16,15 +16,12 @@ tests)
 kbench)
   timeout 600 python tools/kbench.py all > gpurun_out/r02_kbench.jsonl 2> gpurun_out/r02_kbench.err
   echo "kbench rc=$?"
-  B200_PREFILL_KERNEL=umma2 timeout 300 python tools/kbench.py prefill > gpurun_out/r02_kbench_umma2.jsonl 2>&1
-  cat gpurun_out/r02_kbench_umma2.jsonl ;;
+  grep -E "prefill|fa2_varlen" gpurun_out/r02_kbench.jsonl ;;
 ncu)
-  for k in umma umma2; do
-    B200_PREFILL_KERNEL=$k timeout 600 ncu --set full --clock-control none --import-source on \
-      -k regex:prefill_umma -s 4 -c 1 -f -o gpurun_out/r02_prefill_$k python tools/kbench.py prefill16 \
-      > gpurun_out/r02_ncu_$k.log 2>&1
-    echo "ncu $k rc=$?"
-  done ;;
+  timeout 600 ncu --set full --clock-control none --import-source on \
+    -k regex:prefill_umma_kernel -s 4 -c 1 -f -o gpurun_out/r02_prefill_umma python tools/kbench.py prefill16 \
+    > gpurun_out/r02_ncu_prefill.log 2>&1
+  echo "ncu prefill rc=$?" ;;
 sanitize)
   for tool in memcheck racecheck; do
     timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 \
