@@ -187,13 +187,19 @@ def prefill_roofline():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed regions."""
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed regions. The process
+    is started early (its NVML start-up takes driver locks for a few hundred ms: started right before
+    the timed region it randomly stalled the first prefill step by 100-400 ms and with it every TTFT);
+    only rows that arrive after begin() are counted."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_begin = [], None, index, 0.0
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
 
     def start(self):
         try:
@@ -206,7 +212,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -214,7 +220,9 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if t < self.t_begin:
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -365,9 +373,13 @@ def decode_workload(llm, group, B, ctx, K, W, prompt_seed, rank):
     t_submit = time.perf_counter()
     seqs = [llm.add_request(p, sp) for p in prompts]
     prefill_steps = 0
+    step_ms = []
     while llm.scheduler.waiting:
+        t_step = time.perf_counter()
         llm.step()
+        step_ms.append((time.perf_counter() - t_step) * 1e3)
         prefill_steps += 1
+    submit_ms = (t_step - t_submit) * 1e3 - sum(step_ms[:-1]) if step_ms else 0.0   # add_request x B
     ttfts = sorted((s.first_token_time - t_submit) * 1e3 for s in seqs)
     dbg(rank, 'prefill done')
     for _ in range(W):
@@ -397,6 +409,7 @@ def decode_workload(llm, group, B, ctx, K, W, prompt_seed, rank):
     del graph
     dbg(rank, 'replay done')
     return {"e2e_s": e2e_s, "dev_s": dev_s, "ttfts": ttfts, "prefill_steps": prefill_steps,
+            "prefill_step_ms": [round(t, 2) for t in step_ms], "submit_ms": round(submit_ms, 2),
             "h2d_per": (runner.h2d_bytes - h2d0) / K, "d2h_per": (runner.d2h_bytes - d2h0) / K,
             "launches": runner.launches_per_graph.get(B, 0) * K, "ctx_now": ctx + W + K}
 
@@ -559,6 +572,8 @@ def main():
     from nanovllm import LLM
     K, W, B, ctx = args.steps, max(3, args.warmup), args.batch, args.ctx
     max_len = ctx + W + K + 16
+    clocks = ClockSampler(local)
+    clocks.start()
     llm = LLM(args.model, kvcache_block_size=args.block_size, max_num_seqs=B,
               max_model_len=max(4096, max_len), max_num_batched_tokens=16384,
               tensor_parallel_size=world if args.tp else 1, distributed_launch="env",
@@ -566,10 +581,9 @@ def main():
     runner = llm.model_runner
     spec = runner.spec
     group = Group(world)
-    clocks = ClockSampler(local)
     dbg(rank, 'engine built')
     group.barrier()
-    clocks.start()
+    clocks.begin()
     r = decode_workload(llm, group, B, ctx, K, W, rank if not args.tp else 0, rank)
     peak, peak_src = peaks()
     fp8 = args.kv_cache_dtype != "auto"
@@ -593,6 +607,7 @@ def main():
         "e2e": {"value": engines * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": r["h2d_per"],
                 "d2h_bytes_per_step": r["d2h_per"], "ms_per_step": e2e_s / K * 1e3},
         "ttft_p50_ms": ttfts[len(ttfts) // 2], "ttft_max_ms": ttfts[-1], "prefill_steps": r["prefill_steps"],
+        "prefill_step_ms": r["prefill_step_ms"], "submit_ms": r["submit_ms"],
         "prefill_tokens_per_s": engines * B * ctx / prefill_s,
         "gpu_launches": r["launches"],
         "roofline": roof,

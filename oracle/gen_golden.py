@@ -128,16 +128,18 @@ def gen_models():
                                      block_size=16, tokens=toks, top_values=top.values,
                                      top_indices=top.indices,
                                      logit_mean=lg.mean(-1), logit_std=lg.std(-1))
-    # The same configuration with a livelier init (std 0.05, norm weights 1 + 0.1 N(0,1), seed 1):
-    # the N(0, 0.02) model above collapses to one repeated token, which makes "greedy ids identical"
-    # thin evidence; this one emits 32 distinct ids with a median top-1/top-2 margin of 0.25.
-    w = M.seeded_weights(cfg, seed=1, norm_jitter=0.1, std=0.05)
+    # The same configuration with a livelier init (std 0.04, norm weights 1 + 0.1 N(0,1), seed 1) and 64
+    # tokens: the N(0, 0.02) model above collapses to one repeated token, which makes "greedy ids
+    # identical" thin evidence; this one emits ~60 distinct ids with a median top-1/top-2 margin of 0.25.
+    # (Larger init std makes the random model chaotic: at 0.05 the reference's own bf16-rounding attention
+    # and an fp32 evaluation of the same graph already differ by 0.2-0.4 in the logits.)
+    w = M.seeded_weights(cfg, seed=1, norm_jitter=0.1, std=0.04)
     model = build_reference_model(cfg, w)
-    toks, logs = reference_greedy(model, cfg, prompts, 32, 16)
+    toks, logs = reference_greedy(model, cfg, prompts, 64, 16)
     lg = torch.stack(logs)[:, 0]
     top = lg.topk(8, dim=-1)
-    out["qwen3_0_6b_config1_varied"] = dict(seed=1, norm_jitter=0.1, init_std=0.05, prompts=prompts,
-                                            max_tokens=32, block_size=16, tokens=toks,
+    out["qwen3_0_6b_config1_varied"] = dict(seed=1, norm_jitter=0.1, init_std=0.04, prompts=prompts,
+                                            max_tokens=64, block_size=16, tokens=toks,
                                             top_values=top.values, top_indices=top.indices,
                                             logit_mean=lg.mean(-1), logit_std=lg.std(-1))
     return out
