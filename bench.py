@@ -96,6 +96,7 @@ def parse_args():
     ap.add_argument("--tp-model", default="qwen3-32b",
                     help="model of the `tp` object a multi-GPU replica run adds (BASELINE configs[3])")
     ap.add_argument("--no-tp-block", action="store_true", help="multi-GPU replica run without the `tp` object")
+    ap.add_argument("--tp-timeout", type=float, default=420.0, help="seconds before the `tp` object is abandoned")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mem-util", type=float, default=0.7, help="gpu_memory_utilization of the engine")
     ap.add_argument("--cpu-sample-seqs", type=int, default=32)
@@ -496,13 +497,51 @@ def allreduce_microbench(runner, rows, reps=200):
         one()
     torch.cuda.synchronize()
     dist.barrier()
+    # inside a CUDA graph, like the decode step: device time per call, not the host's launch rate
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            one()
+    graph.replay()
+    torch.cuda.synchronize()
+    dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        one()
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
+    del graph
     return form or "nccl", e0.elapsed_time(e1) * 1e3 / reps
+
+
+def tp_engine_measure(args, rank, world, K, W, peak, peak_src, kw):
+    """One tensor-parallel engine over all `world` ranks: decode workload, all-reduce microbench,
+    attention roofline. Returns the `tp` fields that do not need the TP=1 comparison."""
+    from nanovllm import LLM
+    B, ctx = args.batch, args.ctx
+    llm = LLM(args.tp_model, tensor_parallel_size=world, **kw)
+    runner = llm.model_runner
+    r = decode_workload(llm, Group(world), B, ctx, K, W, 0, rank)
+    form, ar_us = allreduce_microbench(runner, B)
+    roof = attention_roofline(runner, Group(world), B, K, world, False, peak, peak_src)
+    L, spec = runner.spec.num_layers, runner.spec
+    weight_bytes = sum(p.numel() * p.element_size() for p in runner.model.parameters())
+    step_bytes = weight_bytes + roof["algorithmic_bytes_per_launch"] * L
+    out = {
+        "tokens_per_s": B * K / r["dev_s"], "ms_per_step": r["dev_s"] / K * 1e3,
+        "e2e_tokens_per_s": B * K / r["e2e_s"], "e2e_ms_per_step": r["e2e_s"] / K * 1e3,
+        "ttft_p50_ms": r["ttfts"][len(r["ttfts"]) // 2], "gpu_launches_per_step": r["launches"] // K,
+        "allreduce_form": form, "allreduce_us": ar_us, "allreduces_per_step": 2 * L,
+        "allreduce_message_bytes": B * spec.hidden_size * 2,
+        "sampling": "vocab-sharded keys + 8 B/row MAX all-reduce" if runner.sharded_sampling else
+                    "logits gathered on rank 0",
+        "attention_us_per_layer": roof["us_per_launch"], "attention_frac_of_hbm_peak": roof["frac"],
+        "per_rank_bytes_per_step": step_bytes,
+        "per_rank_hbm_floor_ms": step_bytes / (peak * 1e9) * 1e3,
+    }
+    del runner
+    release(llm)
+    return out
 
 
 def tp_block(args, rank, world, K, W, peak, peak_src):
@@ -516,28 +555,7 @@ def tp_block(args, rank, world, K, W, peak, peak_src):
               max_num_batched_tokens=16384, distributed_launch="env", gpu_memory_utilization=0.88,
               graph_batch_sizes=(B,), seed=0)
     out = {"model": args.tp_model, "tp": world, "batch": B, "ctx": ctx}
-    llm = LLM(args.tp_model, tensor_parallel_size=world, **kw)
-    runner = llm.model_runner
-    r = decode_workload(llm, Group(world), B, ctx, K, W, 0, rank)
-    form, ar_us = allreduce_microbench(runner, B)
-    roof = attention_roofline(runner, Group(world), B, K, world, False, peak, peak_src)
-    L, spec = runner.spec.num_layers, runner.spec
-    weight_bytes = sum(p.numel() * p.element_size() for p in runner.model.parameters())
-    step_bytes = weight_bytes + roof["algorithmic_bytes_per_launch"] * L
-    out.update({
-        "tokens_per_s": B * K / r["dev_s"], "ms_per_step": r["dev_s"] / K * 1e3,
-        "e2e_tokens_per_s": B * K / r["e2e_s"], "e2e_ms_per_step": r["e2e_s"] / K * 1e3,
-        "ttft_p50_ms": r["ttfts"][len(r["ttfts"]) // 2], "gpu_launches_per_step": r["launches"] // K,
-        "allreduce_form": form, "allreduce_us": ar_us, "allreduces_per_step": 2 * L,
-        "allreduce_message_bytes": B * spec.hidden_size * 2,
-        "sampling": "vocab-sharded keys + 8 B/row MAX all-reduce" if runner.sharded_sampling else
-                    "logits gathered on rank 0",
-        "attention_us_per_layer": roof["us_per_launch"], "attention_frac_of_hbm_peak": roof["frac"],
-        "per_rank_bytes_per_step": step_bytes,
-        "per_rank_hbm_floor_ms": step_bytes / (peak * 1e9) * 1e3,
-    })
-    del runner
-    release(llm)
+    out.update(tp_engine_measure(args, rank, world, K, W, peak, peak_src, kw))
     dist.barrier()
     if rank == 0:
         llm = LLM(args.tp_model, tensor_parallel_size=1, **kw)
@@ -624,10 +642,20 @@ def main():
     if world > 1 and not args.tp and not args.no_tp_block:
         # the replicas above say nothing about the collective design: the same run also measures the
         # tensor-parallel path (BASELINE configs[3]) over all `world` GPUs, with its TP=1 comparison
+        def bail():                       # a hung collective must not cost the replica line
+            line["tp"] = {"error": f"tensor-parallel block did not finish within {args.tp_timeout} s"}
+            if rank == 0:
+                print(json.dumps(line))
+                sys.stdout.flush()
+            os._exit(0)
+        watchdog = threading.Timer(args.tp_timeout, bail)
+        watchdog.daemon = True
+        watchdog.start()
         try:
             line["tp"] = tp_block(args, rank, world, K, W, peak, peak_src)
         except Exception as e:            # symmetric failures only (OOM on every rank); reported, not hidden
             line["tp"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        watchdog.cancel()
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "qwen3-0.6b":
         tps, sec, kind, cores = reference_cpu_step(args.cpu_sample_seqs, ctx, args.block_size, 3, 1, False)
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": cores, "kind": kind,

@@ -24,10 +24,10 @@ quick)   # does the NVLS form survive CUDA-graph decode under torchrun? does the
   run r02_scale_line_n${N}  500 env B200_BENCH_DEBUG=450 $TR --master-port 29613 bench.py --gpus $N --steps 20 --warmup 3
   ;;
 full)
-  run r02_tp${N}_32b_nccl     240 env B200_ALLREDUCE=nccl B200_SHARDED_SAMPLING=0 $TR --master-port 29601 $B
-  run r02_tp${N}_32b_auto     240 $TR --master-port 29602 $B
-  run r02_tp${N}_32b_nvls     240 env B200_ALLREDUCE=nvls B200_BENCH_DEBUG=200 $TR --master-port 29604 $B
-  run r02_tp${N}_32b_nvlsf    240 env B200_ALLREDUCE=nvls_fused B200_BENCH_DEBUG=200 $TR --master-port 29607 $B
+  run r02_tp${N}_32b_forms    560 env B200_BENCH_DEBUG=520 $TR --master-port 29601 tools/tp_forms_bench.py --model ${MODEL:-qwen3-32b} --forms ${FORMS:-auto,nvls_fused,nccl,nvls} --budget-s ${BUDGET:-330}
+  grep -E '^\{' gpurun_out/r02_tp${N}_32b_forms.log | tee -a $S | cut -c1-400
+  ;;
+timeline)
   run r02_tp${N}_32b_timeline 240 $TR --master-port 29605 tools/step_timeline.py --model qwen3-32b --tp --mem-util 0.85 --out gpurun_out/r02_timeline_tp${N}_32b.txt
   ;;
 esac
