@@ -364,6 +364,14 @@ int b200_allreduce_add_rmsnorm_nvls_fused(void* residual, const void* weight, fl
                                           void* const* peer_flags, void* state, int32_t world,
                                           int32_t rank, int32_t dtype, b200_stream_t stream);
 
+/* NVLS one-shot form: every rank pulls the in-switch sum of EVERY row (one multimem.ld_reduce per 16
+ * bytes; this rank's links carry 1 x the message instead of (world-1) x), adds the residual and
+ * normalises locally. One flag barrier per call, no row slicing (any rows <= 1184). */
+int b200_allreduce_add_rmsnorm_nvls_oneshot(void* out, void* residual, const void* weight, float eps,
+                                            int32_t rows, int32_t hidden, const void* mc_partial,
+                                            void* const* peer_flags, void* state, int32_t world,
+                                            int32_t rank, int32_t dtype, b200_stream_t stream);
+
 /* Set-up helpers for the peer buffers (NOT hot path: they allocate / map memory, synchronously).
  * alloc: cudaMalloc + zero; get/open_handle: CUDA IPC (64-byte handle, peer access enabled
  * lazily); all return 0 or a cudaError_t value. */

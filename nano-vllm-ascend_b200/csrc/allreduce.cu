@@ -241,9 +241,15 @@ allreduce_add_rmsnorm_twoshot_kernel(const Ar2Params q, T* __restrict__ out, T* 
       if (r < p.world) reinterpret_cast<uint4*>(q.gather[r])[idx] = y;
   }
   // ---- barrier 2: the last CTA of this rank to finish its pushes tells every peer
-  __threadfence_system();
+  // One fence per CTA, not per thread: bar.sync orders every thread's pushes before thread 0's
+  // gpu-scope fence + ticket; the CTA that draws the last ticket issues the system-scope fence and
+  // the release stores (fences are cumulative in the PTX memory model). 37 k threads each issuing
+  // fence.sys cost several microseconds per call.
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[3], 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_ticket = atomicAdd(&p.state[3], 1u);
+  }
   __syncthreads();
   if (s_ticket == gridDim.x - 1 && threadIdx.x < p.world) {
     __threadfence_system();
@@ -357,9 +363,15 @@ allreduce_add_rmsnorm_nvls_kernel(const ArMcParams q, T* __restrict__ out, T* __
        idx += (int64_t)gridDim.x * blockDim.x)
     multimem_st(mc_out + idx, multimem_ld_reduce_add<T>(mc_in + idx));
   // ---- barrier 2: the last CTA of this rank to finish its stores tells every peer
-  __threadfence_system();
+  // One fence per CTA, not per thread: bar.sync orders every thread's pushes before thread 0's
+  // gpu-scope fence + ticket; the CTA that draws the last ticket issues the system-scope fence and
+  // the release stores (fences are cumulative in the PTX memory model). 37 k threads each issuing
+  // fence.sys cost several microseconds per call.
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[3], 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_ticket = atomicAdd(&p.state[3], 1u);
+  }
   __syncthreads();
   if (s_ticket == gridDim.x - 1 && threadIdx.x < p.world) {
     __threadfence_system();
@@ -394,6 +406,56 @@ allreduce_add_rmsnorm_nvls_kernel(const ArMcParams q, T* __restrict__ out, T* __
       p.state[1] = 0;
       p.state[2] = 0;
       p.state[3] = 0;
+      __threadfence();
+      p.state[0] = epoch;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NVLS one-shot: the one-shot kernel with the world-way pull replaced by ONE multimem.ld_reduce per 16
+// bytes -- every rank asks the switch for the sum of every row (the switch reduces each request; this
+// rank's links carry 1 x the message instead of (world-1) x), then adds the residual and normalises
+// locally. One flag barrier per call (two alternating partial buffers, as the one-shot form), no slicing,
+// so any row count works. Each rank's sums come from its own switch requests.
+template <typename T>
+__global__ void __launch_bounds__(256)
+allreduce_add_rmsnorm_nvls_oneshot_kernel(const ArMcParams q, T* __restrict__ out, T* __restrict__ residual,
+                                          const T* __restrict__ weight, float eps, int hidden) {
+  __shared__ float red[32];
+  __shared__ uint32_t s_ticket;
+  const ArParams& p = q.base;
+  pdl_wait();
+  const uint32_t epoch = p.state[0] + 1;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[2], 1u);
+  __syncthreads();
+  if (s_ticket == 0 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + p.rank, epoch);
+  }
+  if (threadIdx.x < p.world) {
+    const uint32_t* mine = p.flags[p.rank] + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+  const uint4* mc_in = reinterpret_cast<const uint4*>(q.mc_partial);
+  add_rmsnorm_row<T>(blockIdx.x, hidden, out, residual, weight, eps, red, [&](int64_t idx, float (&acc)[8]) {
+    const uint4 y = multimem_ld_reduce_add<T>(mc_in + idx);
+    const uint32_t w[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack2<T>(w[j]);
+      acc[2 * j] = f.x;
+      acc[2 * j + 1] = f.y;
+    }
+  });
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(&p.state[1], 1u);
+    if (done == gridDim.x - 1) {
+      p.state[1] = 0;
+      p.state[2] = 0;
       __threadfence();
       p.state[0] = epoch;
     }
@@ -453,9 +515,15 @@ allreduce_add_rmsnorm_nvls_fused_kernel(const ArMcParams q, T* __restrict__ resi
     __syncthreads();
   }
   // ---- every rank's rows have landed in my `out` region once all peers passed this barrier
-  __threadfence_system();
+  // One fence per CTA, not per thread: bar.sync orders every thread's pushes before thread 0's
+  // gpu-scope fence + ticket; the CTA that draws the last ticket issues the system-scope fence and
+  // the release stores (fences are cumulative in the PTX memory model). 37 k threads each issuing
+  // fence.sys cost several microseconds per call.
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.state[3], 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_ticket = atomicAdd(&p.state[3], 1u);
+  }
   __syncthreads();
   if (s_ticket == gridDim.x - 1 && threadIdx.x < p.world) {
     __threadfence_system();
@@ -654,6 +722,47 @@ extern "C" int b200_allreduce_add_rmsnorm_nvls_fused(void* residual, const void*
   else
     launch_pdl(allreduce_add_rmsnorm_nvls_fused_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
                q, (__half*)residual, (const __half*)weight, eps, hidden);
+  return finish_launch();
+}
+
+extern "C" int b200_allreduce_add_rmsnorm_nvls_oneshot(void* out, void* residual, const void* weight, float eps,
+                                                       int32_t rows, int32_t hidden, const void* mc_partial,
+                                                       void* const* peer_flags, void* state, int32_t world,
+                                                       int32_t rank, int32_t dtype, b200_stream_t stream) {
+  B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
+  B200_RETURN_IF(rows < 0 || hidden <= 0 || world < 2 || world > kMaxWorld || rank < 0 || rank >= world,
+                 B200_ERR_BAD_SHAPE);
+  if (rows == 0) return B200_OK;
+  B200_RETURN_IF(!out || !residual || !weight || !mc_partial || !peer_flags || !state, B200_ERR_NULL_POINTER);
+  B200_RETURN_IF(hidden % 8 != 0 || !aligned16(out) || !aligned16(residual) || !aligned16(weight) ||
+                     !aligned16(mc_partial),
+                 B200_ERR_MISALIGNED);
+  B200_RETURN_IF(hidden > 8 * 256 * 4, B200_ERR_UNSUPPORTED);
+  ArMcParams q;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    q.base.bufs[r] = nullptr;
+    q.base.flags[r] = nullptr;
+  }
+  for (int r = 0; r < world; ++r) {
+    B200_RETURN_IF(!peer_flags[r], B200_ERR_NULL_POINTER);
+    q.base.flags[r] = reinterpret_cast<uint32_t*>(peer_flags[r]);
+  }
+  q.base.state = reinterpret_cast<uint32_t*>(state);
+  q.base.world = world;
+  q.base.rank = rank;
+  q.mc_partial = mc_partial;
+  q.mc_gather = nullptr;
+  q.local_gather = nullptr;
+  q.rows = rows;
+  // one CTA per row, all spinning on the start barrier: rows <= the co-resident capacity (8 CTAs/SM)
+  B200_RETURN_IF(rows > 148 * 8, B200_ERR_UNSUPPORTED);
+  if (dtype == B200_DTYPE_BF16)
+    launch_pdl(allreduce_add_rmsnorm_nvls_oneshot_kernel<__nv_bfloat16>, dim3(rows), dim3(256), 0,
+               (cudaStream_t)stream, q, (__nv_bfloat16*)out, (__nv_bfloat16*)residual,
+               (const __nv_bfloat16*)weight, eps, hidden);
+  else
+    launch_pdl(allreduce_add_rmsnorm_nvls_oneshot_kernel<__half>, dim3(rows), dim3(256), 0, (cudaStream_t)stream,
+               q, (__half*)out, (__half*)residual, (const __half*)weight, eps, hidden);
   return finish_launch();
 }
 

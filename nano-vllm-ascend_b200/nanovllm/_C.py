@@ -86,6 +86,9 @@ PROTOTYPES = {
     "b200_allreduce_add_rmsnorm_nvls_fused": (c_int32, [c_void_p, c_void_p, c_float, c_int32, c_int32,
                                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                                         c_int32, c_int32, c_void_p]),
+    "b200_allreduce_add_rmsnorm_nvls_oneshot": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int32,
+                                                          c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                                          c_int32, c_int32, c_void_p]),
     "b200_comm_alloc": (c_int32, [c_size_t, c_void_p]),
     "b200_comm_free": (c_int32, [c_void_p]),
     "b200_comm_get_handle": (c_int32, [c_void_p, c_void_p]),

@@ -11,7 +11,7 @@ torch.distributed only to exchange the 64-byte IPC handles.
 Form selection (``mode``): one-shot while (world-1) x message <= 4 MB, two-shot beyond (both validated on
 hardware inside the engine, eager and CUDA-graph decode, r02), NCCL for shapes neither takes.
 ``B200_ALLREDUCE`` forces one form for every shape it can take -- a measurement aid for A/B runs:
-``nccl`` | ``oneshot`` | ``twoshot`` | ``nvls`` | ``nvls_fused``. The two NVLS values make the region a
+``nccl`` | ``oneshot`` | ``twoshot`` | ``nvls`` | ``nvls_fused`` | ``nvls_one``. The NVLS values make the region a
 torch symmetric-memory allocation (plumbing: cuMemCreate + handle exchange + cuMulticastBindMem done by
 ``torch.distributed._symmetric_memory``), which yields the same per-rank peer pointers PLUS one multicast
 address for the whole region; messages then go through b200_allreduce_add_rmsnorm_nvls[_fused]
@@ -50,9 +50,10 @@ class PeerAllReduce:
         self.multicast_ptr = 0       # multicast address of the region (NVLS), 0 = not available
         self._symm = None
         self.forced = os.environ.get("B200_ALLREDUCE", "auto").lower()
-        if self.forced not in ("auto", "nccl", "oneshot", "twoshot", "nvls", "nvls_fused"):
-            raise ValueError(f"B200_ALLREDUCE={self.forced!r}: expected auto|nccl|oneshot|twoshot|nvls|nvls_fused")
-        if self.forced in ("nvls", "nvls_fused"):
+        if self.forced not in ("auto", "nccl", "oneshot", "twoshot", "nvls", "nvls_fused", "nvls_one"):
+            raise ValueError(f"B200_ALLREDUCE={self.forced!r}: expected "
+                             "auto|nccl|oneshot|twoshot|nvls|nvls_fused|nvls_one")
+        if self.forced in ("nvls", "nvls_fused", "nvls_one"):
             self._map_symmetric(total)
         else:
             self._map_ipc(total)
@@ -113,6 +114,8 @@ class PeerAllReduce:
         if self.forced == "nccl" or nbytes > self.max_bytes or hidden % 8 != 0 or hidden > 8192:
             return None
         sliced_ok = rows >= self.world           # the row-sliced forms need a row per rank
+        if self.forced == "nvls_one":
+            return "nvls_one" if rows <= 148 * 8 else None
         if self.forced in ("nvls", "nvls_fused"):
             return self.forced if sliced_ok else "one"
         if self.forced == "twoshot":
@@ -155,7 +158,12 @@ class PeerAllReduce:
             return out, residual
         if out is None:
             out = torch.empty_like(view)
-        if mode == "nvls":
+        if mode == "nvls_one":
+            _C.check(self.lib.b200_allreduce_add_rmsnorm_nvls_oneshot(
+                out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,
+                self.multicast_ptr + parity * self.max_bytes, self._flags, self._state, self.world,
+                self.rank, _dt(view), _stream()), "b200_allreduce_add_rmsnorm_nvls_oneshot")
+        elif mode == "nvls":
             mc = self.multicast_ptr
             _C.check(self.lib.b200_allreduce_add_rmsnorm_nvls(
                 out.data_ptr(), residual.data_ptr(), weight.data_ptr(), float(eps), rows, hidden,

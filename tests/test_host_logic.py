@@ -612,7 +612,8 @@ def test_fused_allreduce_form_selection():
     c.world = 8
     for forced, big, small, few_rows in (("nccl", None, None, None), ("oneshot", "one", "one", "one"),
                                          ("twoshot", "two", "two", "one"), ("nvls", "nvls", "nvls", "one"),
-                                         ("nvls_fused", "nvls_fused", "nvls_fused", "one")):
+                                         ("nvls_fused", "nvls_fused", "nvls_fused", "one"),
+                                         ("nvls_one", "nvls_one", "nvls_one", "nvls_one")):
         c.forced = forced
         assert (c.mode(256, 5120, 2), c.mode(256, 1024, 2), c.mode(4, 8192, 2)) == (big, small, few_rows), forced
         assert c.mode(4096, 5120, 2) is None        # a forced form never takes what does not fit the region

@@ -66,6 +66,9 @@ _NVLS_CASES = [(256, 5120, "nvls"), (37, 5120, "nvls"), (8, 2048, "one"), (2, 10
 # the one-pass NVLS form with a row-sliced residual, alone and mixed with the other forms
 _NVLS_FUSED_CASES = [(256, 5120, "nvls_fused"), (37, 5120, "nvls_fused"), (2, 1024, "nvls_fused"),
                      (8, 2048, "one"), (255, 4096, "nvls_fused"), (256, 1024, "nvls"), (3, 8192, "nvls_fused")]
+# the one-barrier NVLS form (every rank pulls every row's in-switch sum), any row count, mixed with the others
+_NVLS_ONE_CASES = [(256, 5120, "nvls_one"), (1, 1024, "nvls_one"), (37, 5120, "nvls_one"), (8, 2048, "one"),
+                   (256, 1024, "nvls"), (255, 8192, "nvls_one"), (64, 2048, "two"), (3, 128, "nvls_one")]
 
 
 def _ar_worker(rank, world, port, out_q, cases):
@@ -153,3 +156,4 @@ def test_fused_peer_allreduce_nvls_kernel(monkeypatch):
     monkeypatch.setenv("B200_ALLREDUCE", "nvls")      # symmetric-memory region (inherited by the workers)
     assert _run_ar_workers(2, 28035, _NVLS_CASES) == {0: True, 1: True}
     assert _run_ar_workers(2, 28037, _NVLS_FUSED_CASES) == {0: True, 1: True}
+    assert _run_ar_workers(2, 28039, _NVLS_ONE_CASES) == {0: True, 1: True}
