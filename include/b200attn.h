@@ -139,6 +139,17 @@ int b200_paged_decode_attn_fp8(void* out, const void* q, const void* k_cache, co
                                size_t workspace_bytes, int32_t num_ctas, int32_t dtype,
                                b200_stream_t stream);
 
+/* Paged e4m3 cache -> packed 16-bit K/V for the prefill kernel (prefix-cache-hit / chunked prefill
+ * over an fp8 cache; extension, the reference's caches are always the model dtype). For sequence i,
+ * rows cu_seqlens_k[i] .. cu_seqlens_k[i+1]-1 of k_out / v_out [total_k, num_kv_heads*head_dim]
+ * receive its first cached tokens, gathered through block_tables[i] and multiplied by k_scale /
+ * v_scale (fp32, one rounding to dtype). Table entries outside [0, num_blocks) give zero rows. */
+int b200_gather_dequant_fp8(void* k_out, void* v_out, const void* k_cache, const void* v_cache,
+                            const int32_t* block_tables, const int32_t* cu_seqlens_k, int32_t num_seqs,
+                            int32_t max_seqlen_k, int32_t block_table_stride, int32_t num_blocks,
+                            int32_t block_size, int32_t num_kv_heads, int32_t head_dim, float k_scale,
+                            float v_scale, int32_t dtype, b200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------
  * K4/K5  varlen causal prefill flash-attention.
  * Replaces: npu_fused_infer_attention_score_v2 TND, sparse_mode=3  layers/attention.py:49-59

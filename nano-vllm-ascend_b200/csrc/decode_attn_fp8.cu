@@ -467,6 +467,48 @@ kv_scatter_fp8_kernel(const uint4* __restrict__ key, const uint4* __restrict__ v
   }
 }
 
+// ------------------------------------------------------------------ paged fp8 cache -> packed 16-bit K/V
+// Prefix-hit / chunked prefill over an e4m3 cache: the tcgen05 prefill kernel multiplies 16-bit
+// operands, so the cached tokens of every sequence are first gathered through its block table and
+// de-quantised (x = e4m3 * scale, exact in fp32, one rounding to T) into packed [total_k, Hkv*D]
+// buffers, which the packed-K/V prefill path then reads. One 8-byte load (8 e4m3) -> one 16-byte store.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_dequant_fp8_kernel(uint4* __restrict__ k_out, uint4* __restrict__ v_out,
+                          const uint2* __restrict__ k_cache, const uint2* __restrict__ v_cache,
+                          const int32_t* __restrict__ block_tables, const int32_t* __restrict__ cu_k,
+                          int bt_stride, int num_blocks, int block_size, int vec_per_row, float k_scale,
+                          float v_scale) {
+  pdl_wait();
+  const int seq = blockIdx.y;
+  const int k0 = cu_k[seq], len = cu_k[seq + 1] - k0;
+  const int64_t total = (int64_t)len * vec_per_row * 2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int vec = (int)(idx % vec_per_row);
+    const int64_t rest = idx / vec_per_row;
+    const int which = (int)(rest & 1);
+    const int tok = (int)(rest >> 1);
+    const int blk = block_tables[(int64_t)seq * bt_stride + tok / block_size];
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (blk >= 0 && blk < num_blocks) {
+      const int64_t slot = (int64_t)blk * block_size + tok % block_size;
+      const uint2 x = (which == 0 ? k_cache : v_cache)[slot * vec_per_row + vec];
+      const float sc = which == 0 ? k_scale : v_scale;
+      const uint32_t w[2] = {x.x, x.y};
+      uint32_t r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t h2 = e4m3x2_to_f16x2((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+        r[j] = pack2<T>(__fmul_rn(f.x, sc), __fmul_rn(f.y, sc));
+      }
+      o = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    (which == 0 ? k_out : v_out)[(int64_t)(k0 + tok) * vec_per_row + vec] = o;
+  }
+}
+
 template <typename T, int D>
 static int decode_fp8_launch_d(int hkv_cta, const CUtensorMap& mk, const CUtensorMap& mv,
                                const DecodeParams& p, float v_scale, int grid, cudaStream_t stream) {
@@ -631,5 +673,42 @@ extern "C" int b200_reshape_and_cache_fp8(const void* key, const void* value, vo
     else B200_LAUNCH_SCATTER8(__half, false);
   }
 #undef B200_LAUNCH_SCATTER8
+  return finish_launch();
+}
+
+extern "C" int b200_gather_dequant_fp8(void* k_out, void* v_out, const void* k_cache, const void* v_cache,
+                                       const int32_t* block_tables, const int32_t* cu_seqlens_k,
+                                       int32_t num_seqs, int32_t max_seqlen_k, int32_t block_table_stride,
+                                       int32_t num_blocks, int32_t block_size, int32_t num_kv_heads,
+                                       int32_t head_dim, float k_scale, float v_scale, int32_t dtype,
+                                       b200_stream_t stream) {
+  using namespace b200;
+  B200_RETURN_IF(dtype != B200_DTYPE_BF16 && dtype != B200_DTYPE_F16, B200_ERR_BAD_DTYPE);
+  B200_RETURN_IF(num_seqs < 0 || max_seqlen_k < 0 || num_kv_heads <= 0 || head_dim <= 0 ||
+                     block_table_stride <= 0 || num_blocks <= 0 || block_size <= 0,
+                 B200_ERR_BAD_SHAPE);
+  B200_RETURN_IF((num_kv_heads * head_dim) % 8 != 0, B200_ERR_UNSUPPORTED);
+  B200_RETURN_IF(!(k_scale > 0.f) || !(v_scale > 0.f), B200_ERR_BAD_SHAPE);
+  if (num_seqs == 0 || max_seqlen_k == 0) return B200_OK;
+  B200_RETURN_IF(!k_out || !v_out || !k_cache || !v_cache || !block_tables || !cu_seqlens_k,
+                 B200_ERR_NULL_POINTER);
+  B200_RETURN_IF(!aligned16(k_out) || !aligned16(v_out) || (reinterpret_cast<uintptr_t>(k_cache) & 7) ||
+                     (reinterpret_cast<uintptr_t>(v_cache) & 7),
+                 B200_ERR_MISALIGNED);
+  B200_RETURN_IF(num_seqs > 65535, B200_ERR_UNSUPPORTED);
+  const int vec_per_row = num_kv_heads * head_dim / 8;
+  const int64_t per_seq = (int64_t)max_seqlen_k * vec_per_row * 2;
+  int gx = (int)((per_seq + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == B200_DTYPE_BF16)
+    launch_pdl(gather_dequant_fp8_kernel<__nv_bfloat16>, dim3(gx, num_seqs), dim3(256), 0, s, (uint4*)k_out,
+               (uint4*)v_out, (const uint2*)k_cache, (const uint2*)v_cache, block_tables, cu_seqlens_k,
+               block_table_stride, num_blocks, block_size, vec_per_row, k_scale, v_scale);
+  else
+    launch_pdl(gather_dequant_fp8_kernel<__half>, dim3(gx, num_seqs), dim3(256), 0, s, (uint4*)k_out,
+               (uint4*)v_out, (const uint2*)k_cache, (const uint2*)v_cache, block_tables, cu_seqlens_k,
+               block_table_stride, num_blocks, block_size, vec_per_row, k_scale, v_scale);
   return finish_launch();
 }

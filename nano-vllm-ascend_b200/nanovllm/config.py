@@ -114,9 +114,6 @@ class Config:
         assert self.kvcache_block_size % 16 == 0
         assert 1 <= self.tensor_parallel_size <= 8
         assert self.kv_cache_dtype in ("auto", "fp8", "fp8_e4m3"), self.kv_cache_dtype
-        if self.kv_cache_dtype != "auto" and (self.prefix_hit_prefill or self.chunked_prefill):
-            raise ValueError("prefix_hit_prefill / chunked_prefill read K/V back from the cache with the "
-                             "prefill kernel, which takes 16-bit caches only; use kv_cache_dtype='auto'")
         if self.hf_config is None:
             if os.path.isdir(self.model):
                 from transformers import AutoConfig

@@ -62,7 +62,16 @@ class Attention(nn.Module):
         if context.is_prefill:
             if context.paged_prefill:
                 if self.fp8_cache:
-                    raise NotImplementedError("paged (prefix-hit) prefill over an fp8 KV cache")
+                    # the tcgen05 kernel multiplies 16-bit operands: gather + de-quantise the cached
+                    # tokens into packed K/V first (this step's own rows were just quantised into the
+                    # cache, so every key is read at cache precision, like the decode steps that follow)
+                    k, v = ops.gather_dequant_fp8(self.k_cache, self.v_cache, context.block_tables,
+                                                  context.cu_seqlens_k, context.max_seqlen_k,
+                                                  self.num_kv_heads, self.head_dim, self.k_scale,
+                                                  self.v_scale, dtype=q.dtype)
+                    return ops.prefill_varlen_attn(q, k, v, context.cu_seqlens_q, context.cu_seqlens_k,
+                                                   context.max_seqlen_q, context.max_seqlen_k, self.scale,
+                                                   self.num_kv_heads)
                 return ops.prefill_varlen_attn(q, self.k_cache, self.v_cache, context.cu_seqlens_q,
                                                context.cu_seqlens_k, context.max_seqlen_q,
                                                context.max_seqlen_k, self.scale, self.num_kv_heads,

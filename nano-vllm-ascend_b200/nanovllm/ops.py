@@ -174,6 +174,30 @@ def paged_decode_attn_fp8(q, k_cache, v_cache, block_tables, context_lens, scale
     return out
 
 
+def gather_dequant_fp8(k_cache, v_cache, block_tables, cu_seqlens_k, max_seqlen_k, num_kv_heads, head_dim,
+                       k_scale=1.0, v_scale=1.0, dtype=torch.bfloat16, total_k=None):
+    """Paged e4m3 caches -> packed [total_k, Hkv, D] K and V in `dtype` (prefix-hit / chunked prefill over
+    an fp8 cache). total_k: number of packed rows (= cu_seqlens_k[-1]); when None it is bounded by
+    num_seqs * max_seqlen_k so that no device value has to be read back."""
+    _need_cuda(k_cache, v_cache, block_tables, cu_seqlens_k)
+    if not (_is_fp8_cache(k_cache) and _is_fp8_cache(v_cache)):
+        raise TypeError("fp8 KV caches must be uint8 or float8_e4m3fn tensors")
+    if block_tables.dtype != torch.int32 or block_tables.stride(1) != 1 or cu_seqlens_k.dtype != torch.int32:
+        raise TypeError("block_tables must be row-major int32, cu_seqlens_k int32")
+    num_seqs = cu_seqlens_k.numel() - 1
+    nb, bs = _cache_dims(k_cache, num_kv_heads * head_dim)
+    rows = int(total_k) if total_k is not None else num_seqs * int(max_seqlen_k)
+    # zeros, not empty: rows past the last sequence are inside the prefill kernel's TMA bounds, and a
+    # masked key's probability 0 times a stale NaN pattern in V would poison the output row
+    k = torch.zeros(rows, num_kv_heads, head_dim, dtype=dtype, device=k_cache.device)
+    v = torch.zeros_like(k)
+    _C.check(_C.load().b200_gather_dequant_fp8(
+        k.data_ptr(), v.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), block_tables.data_ptr(),
+        cu_seqlens_k.data_ptr(), num_seqs, int(max_seqlen_k), block_tables.stride(0), nb, bs, num_kv_heads,
+        head_dim, float(k_scale), float(v_scale), _dt(k), _stream()), "b200_gather_dequant_fp8")
+    return k, v
+
+
 _prefill_ws: dict = {}
 
 

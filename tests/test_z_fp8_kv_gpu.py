@@ -187,3 +187,48 @@ def test_fp8_engine_tracks_bf16_engine(fp8_alive):
     assert all(len(o) == 8 and all(0 <= t < 512 for t in o) for o in outs["fp8"])
     agree = sum(x == y for a, b in zip(outs["auto"], outs["fp8"]) for x, y in zip(a[:4], b[:4]))
     assert agree >= 8, outs          # of 16 positions; e4m3 noise (2^-4 relative per element) flips few
+
+
+@pytest.mark.parametrize("G,D,bs,dtype,scales", [(8, 128, 16, BF, (1.0, 1.0)), (2, 64, 32, torch.float16, (0.25, 3.0)),
+                                                  (1, 128, 256, BF, (2.0, 0.5))])
+def test_fp8_gather_dequant_bit_exact(fp8_alive, G, D, bs, dtype, scales):
+    """b200_gather_dequant_fp8: the cached tokens of every sequence, gathered through its block table and
+    de-quantised -- bit-exact against the oracle's dequantize_e4m3 (exact fp32 product, one rounding)."""
+    lens = [1, 17, 300, 64, 5]
+    _, kc, vc, _, bt = _fp8_case(len(lens), G, G, D, bs, lens, seed=bs + D, k_scale=scales[0], v_scale=scales[1])
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    nb = kc.shape[0]
+    k, v = _ops().gather_dequant_fp8(kc.cuda().view(nb, bs, G * D), vc.cuda().view(nb, bs, G * D), bt.cuda(),
+                                     cu.cuda(), max(lens), G, D, scales[0], scales[1], dtype=dtype)
+    assert k.shape[0] == len(lens) * max(lens)
+    kd, vd = A.dequantize_e4m3(kc, scales[0], dtype), A.dequantize_e4m3(vc, scales[1], dtype)
+    for i, n in enumerate(lens):
+        for t in (0, n // 2, n - 1):
+            blk = int(bt[i, t // bs])
+            assert torch.equal(k[int(cu[i]) + t].cpu(), kd[blk, t % bs]), (i, t)
+            assert torch.equal(v[int(cu[i]) + t].cpu(), vd[blk, t % bs]), (i, t)
+    assert torch.count_nonzero(k[int(cu[-1]):]) == 0          # rows past the last sequence stay zero
+
+
+def test_fp8_chunked_and_prefix_hit_prefill(fp8_alive):
+    """kv_cache_dtype="fp8" with chunked prefill / true prefix-hit prefill (r01 rejected the combination):
+    later windows read the earlier ones back from the e4m3 cache through gather + de-quantise. Same
+    workload as the 16-bit chunked-prefill test; tokens may only drift from the un-chunked fp8 run where
+    logits nearly tie (the un-chunked prefill attends over un-quantised K/V of its own step)."""
+    import random
+    from nanovllm import LLM, SamplingParams
+    rnd = random.Random(12)
+    prompts = [[rnd.randint(0, 511) for _ in range(n)] for n in (300, 40, 17, 200, 129)]
+    prompts.append(prompts[0][:160] + [3] * 30)            # shares 10 full blocks with the first prompt
+    sp = SamplingParams(temperature=1.0, max_tokens=8, ignore_eos=True, greedy=True)
+    outs = []
+    for kw in (dict(max_num_batched_tokens=1024), dict(max_num_batched_tokens=128, chunked_prefill=True),
+               dict(max_num_batched_tokens=1024, prefix_hit_prefill=True)):
+        llm = LLM("tiny-qwen3", seed=3, norm_jitter=0.1, kvcache_block_size=16, max_num_seqs=8,
+                  max_model_len=512, num_kvcache_blocks=128, kv_cache_dtype="fp8", **kw)
+        outs.append([o["token_ids"] for o in llm.generate(prompts, sp, use_tqdm=False)])
+        llm.exit()
+    for other in outs[1:]:
+        assert all(len(o) == 8 and all(0 <= t < 512 for t in o) for o in other)
+        agree = sum(x == y for a, b in zip(outs[0], other) for x, y in zip(a[:3], b[:3]))
+        assert agree >= 12, (agree, outs[0], other)          # of 18 positions
