@@ -177,3 +177,37 @@ def test_moe_kernel_rounding_chain_reproduces_reference(golden_moe):
         d = (out.float() - c["out"].float()).abs()
         assert (d == 0).float().mean() >= 0.999, (name, float((d == 0).float().mean()))
         assert d.max() <= 2 ** -7 * c["out"].float().abs().max(), (name, float(d.max()))
+
+
+def test_reference_archive_is_the_unmodified_reference_and_runs():
+    """oracle/_ref/reference_path.zip (packed by oracle/stage_ref.py at build time; what the CPU arm of
+    bench.py imports on the GPU box): every file's SHA-256 equals the manifest's and, where the reference
+    tree is present, the tree's; the reference's own Qwen3ForCausalLM decodes a step straight from it."""
+    import hashlib
+    import json
+    import os
+    import subprocess
+    import sys
+    import zipfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "reference_path.zip")
+    if not os.path.isfile(path):
+        import pytest
+        pytest.skip("no packed reference (run __graft_entry__.build() where /root/reference exists)")
+    with zipfile.ZipFile(path) as z:
+        manifest = json.loads(z.read("MANIFEST.json"))["sha256"]
+        assert len(manifest) >= 15
+        for rel, digest in manifest.items():
+            data = z.read(rel)
+            assert hashlib.sha256(data).hexdigest() == digest, rel
+            src = os.path.join("/root/reference", rel)
+            if os.path.isfile(src):
+                with open(src, "rb") as f:
+                    assert f.read() == data, f"{rel} differs from the reference tree"
+    env = dict(os.environ, B200_REFERENCE_DIR="archive")
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_runtime", "--seqs", "2", "--ctx", "48", "--steps", "1",
+                        "--warmup", "0", "--threads", "4"], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["source"].endswith("reference_path.zip") and out["tokens_per_s"] > 0
