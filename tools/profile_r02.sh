@@ -24,10 +24,11 @@ ncu)
   echo "ncu prefill rc=$?" ;;
 sanitize)
   for tool in memcheck racecheck; do
+    K="decode_ragged or decode_golden or prefill_golden or prefill_ragged or kv_scatter_golden or prefill_paged or prefill_split or qknorm_rope_cache or layers_golden or fp8_gather or fp8_scatter"
+    echo "# compute-sanitizer --tool $tool python -m pytest tests/test_kernels_gpu.py tests/test_z_fp8_kv_gpu.py -k \"$K\"" > gpurun_out/r02_sanitizer_$tool.log
     timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 \
-      python -m pytest tests/test_kernels_gpu.py -q -x \
-      -k "decode_ragged or decode_golden or prefill_golden or prefill_ragged or kv_scatter_golden or prefill_paged or qknorm_rope_cache or layers_golden" \
-      > gpurun_out/r02_sanitizer_$tool.log 2>&1
+      python -m pytest tests/test_kernels_gpu.py tests/test_z_fp8_kv_gpu.py -q -x -k "$K" \
+      >> gpurun_out/r02_sanitizer_$tool.log 2>&1
     echo "sanitizer $tool rc=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/r02_sanitizer_$tool.log | tail -n 2 | tr '\n' ' ')"
   done ;;
 esac
