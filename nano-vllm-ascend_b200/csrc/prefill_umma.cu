@@ -36,8 +36,6 @@
 // causal skipping; tensor-pipe bound.
 #include "umma.cuh"
 
-#include <type_traits>
-
 namespace b200 {
 
 struct PrefillUmmaParams {
@@ -56,22 +54,6 @@ struct PrefillUmmaParams {
 };
 
 constexpr int kUBM = 128, kUBN = 128, kUStages = 2, kUThreads = 320;
-
-// 2^x on the FMA/ALU pipes instead of MUFU.EX2 (16 results per clock per SM, the softmax warpgroups'
-// tightest resource: 128 x 128 exponentials per tile = 1024 cycles): x = n + f with n = round(x) taken
-// from the low mantissa bits of x + 1.5 * 2^23, 2^f by a degree-3 minimax polynomial on [-0.5, 0.5]
-// (max relative error 7.5e-5; P is rounded to 16 bits, 3.9e-3), 2^n added into the exponent field.
-// 9 issue slots against one slot + 8 cycles of the MUFU pipe, so it pays for about a quarter of the
-// elements (the FA4 trick). Inputs below -125 give ~2^-125 instead of 0: only used on unmasked tiles.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = __fadd_rn(x, 12582912.f);
-  const float f = __fsub_rn(x, __fsub_rn(t, 12582912.f));
-  float p = fmaf(0.0551716499f, f, 0.2426111251f);
-  p = fmaf(p, f, 0.6932609677f);
-  p = fmaf(p, f, 0.9999280572f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 
 template <typename T, int D>
 __global__ void __launch_bounds__(kUThreads, 1)
@@ -291,8 +273,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int n0 = (j_lo + j) * kUBN;
       // mask (warp-uniform test: does this tile touch the diagonal or the end of the keys?)
       const int warp_row0 = m0 + t * kUBM + (warp & 3) * 32;
-      const bool masked_tile = n0 + kUBN > Lk || n0 + kUBN - 1 > warp_row0 + off;
-      if (masked_tile) {
+      if (n0 + kUBN > Lk || n0 + kUBN - 1 > warp_row0 + off) {
         const int limit = min(Lk - 1, qrow + off) - n0;   // last visible key (tile-relative)
 #pragma unroll
         for (int c = 0; c < 128; ++c)
@@ -327,30 +308,21 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // P(j): 128 keys -> 64 packed columns over S[t] columns [0, 64); this thread's S row is
       // already in registers, other rows live in other TMEM lanes. Packed in place: element i of
       // chunk 2h was consumed at iteration i/2.
-      // One pair in four goes through ex2_poly on unmasked tiles (masked tiles hold -inf entries, which
-      // must become exactly 0).
-      auto exps = [&](auto poly) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = h * 64 + 2 * i;
-            const float x0 = fmaf(__uint_as_float(sr[c >> 5][c & 31]), sl2, -mb);
-            const float x1 = fmaf(__uint_as_float(sr[(c + 1) >> 5][(c + 1) & 31]), sl2, -mb);
-            const bool use_poly = decltype(poly)::value && (i & 3) == 3;
-            const float e0 = use_poly ? ex2_poly(x0) : ex2_approx(x0);
-            const float e1 = use_poly ? ex2_poly(x1) : ex2_approx(x1);
-            sum += e0 + e1;
-            sr[2 * h][i] = pack2<T>(e0, e1);
-          }
-          umma::st32(s_addr + h * 32, sr[2 * h]);
-          umma::wait_st();
-          umma::fence_before_sync();
-          mbar_arrive(&p_full[2 * t + h]);          // PV of these 64 keys may start
+        for (int i = 0; i < 32; ++i) {
+          const int c = h * 64 + 2 * i;
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c >> 5][c & 31]), sl2, -mb));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sr[(c + 1) >> 5][(c + 1) & 31]), sl2, -mb));
+          sum += e0 + e1;
+          sr[2 * h][i] = pack2<T>(e0, e1);
         }
-      };
-      if (masked_tile) exps(std::false_type{});
-      else exps(std::true_type{});
+        umma::st32(s_addr + h * 32, sr[2 * h]);
+        umma::wait_st();
+        umma::fence_before_sync();
+        mbar_arrive(&p_full[2 * t + h]);          // PV of these 64 keys may start
+      }
       l_run += sum;
     }
     // ---- epilogue: O / l -> global, or (split-KV) the un-normalised partial -> workspace
