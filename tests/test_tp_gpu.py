@@ -15,14 +15,14 @@ def _need_gpus(n):
         pytest.skip(f"needs {n} GPUs, have {torch.cuda.device_count()}")
 
 
-def _run(tp, prompts, enforce_eager, port, allreduce="auto", sharded_sampling="1"):
+def _run(tp, prompts, enforce_eager, port, allreduce="auto", sharded_sampling="1", model="tiny-qwen3"):
     from nanovllm import LLM, SamplingParams
     # read by comm.PeerAllReduce / ModelRunner at construction, in this process and in the spawned workers
     saved = {k: os.environ.get(k) for k in ("B200_ALLREDUCE", "B200_SHARDED_SAMPLING")}
     os.environ["B200_ALLREDUCE"] = allreduce
     os.environ["B200_SHARDED_SAMPLING"] = sharded_sampling
     try:
-        llm = LLM("tiny-qwen3", seed=3, norm_jitter=0.1, kvcache_block_size=16, max_num_seqs=8,
+        llm = LLM(model, seed=3, norm_jitter=0.1, kvcache_block_size=16, max_num_seqs=8,
                   max_model_len=256, max_num_batched_tokens=1024, num_kvcache_blocks=128,
                   tensor_parallel_size=tp, enforce_eager=enforce_eager, hccl_port=port)
         outs = llm.generate(prompts, SamplingParams(temperature=1.0, max_tokens=24, ignore_eos=True,
@@ -51,6 +51,23 @@ def test_tp2_matches_tp1(enforce_eager, allreduce, sharded_sampling):
     # the sharded sums are reassociated (two partial products + all-reduce), so a token may only
     # differ where the logits nearly tie; the tiny model's margins are >= 0.1, far above that
     assert got == want
+
+
+@pytest.mark.parametrize("enforce_eager", [True, False])
+def test_ep2_moe_matches_single_gpu(enforce_eager):
+    """Sparse-MoE stack on 2 GPUs: attention tensor-parallel by heads, experts placed WHOLE (E/2 per rank,
+    layers/moe.py), the layer's partial sums completed by the fused all-reduce + add + RMSNorm -- against
+    the single-GPU engine (which tests/test_moe_gpu.py pins to the reference-generated greedy run)."""
+    _need_gpus(2)
+    rnd = random.Random(9)
+    prompts = [[rnd.randint(0, 511) for _ in range(n)] for n in (18, 7, 33, 16)]
+    want = _run(1, prompts, True, next(_PORTS), model="tiny-qwen3-moe")
+    got = _run(2, prompts, enforce_eager, next(_PORTS), model="tiny-qwen3-moe")
+    # per-rank partial sums are reassociated (4 of 8 experts each + all-reduce): ids may only part where
+    # logits nearly tie; require the first 6 tokens of every sequence and >= 90 % overall
+    assert [g[:6] for g in got] == [w[:6] for w in want]
+    same = sum(a == b for g, w in zip(got, want) for a, b in zip(g, w))
+    assert same >= 0.9 * sum(len(w) for w in want), (got, want)
 
 
 _ONE_SHOT_CASES = [(256, 1024, None), (1, 1024, None), (37, 5120, None), (256, 128, None), (5, 1024, None),
