@@ -107,19 +107,20 @@ def parse_args():
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as f:
-            d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError, KeyError, TypeError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def tensor_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as f:
             return float(json.load(f)["bf16_tflops"]), "measured burst cuBLAS bf16 (MEASURED_PEAKS.json)"
-    return 1590.0, "fallback (B200_PROFILING.md)"
+    except (OSError, ValueError, KeyError, TypeError):
+        return 1590.0, "fallback (B200_PROFILING.md)"
 
 
 def prefill_roofline():
@@ -286,10 +287,17 @@ def reference_cpu_step(n_seqs, ctx, block_size, steps, warmup, in_process):
     r = subprocess.run([sys.executable, "-m", "oracle.ref_runtime", "--seqs", str(n_seqs), "--ctx", str(ctx),
                         "--block-size", str(block_size), "--steps", str(steps), "--warmup", str(warmup)],
                        cwd=ROOT, capture_output=True, text=True, timeout=1200)
-    if r.returncode != 0:
-        raise RuntimeError("reference CPU arm failed:\n" + r.stderr[-3000:])
-    d = json.loads(r.stdout.strip().splitlines()[-1])
-    return d["tokens_per_s"], d["s_per_step"], "reference", d["threads"]
+    try:
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr[-2000:])
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return d["tokens_per_s"], d["s_per_step"], "reference", d["threads"]
+    except (RuntimeError, ValueError, KeyError, IndexError) as e:
+        # the reference's modules could not be run here: say so and time the oracle port instead
+        print(f"bench.py: reference CPU arm failed ({type(e).__name__}: {str(e)[-300:]}); "
+              f"timing the oracle port", file=sys.stderr)
+        tps, sec = cpu_reference_step(n_seqs, ctx, block_size, steps, warmup, cores)
+        return tps, sec, "port", torch.get_num_threads()
 
 
 def cpu_sample_text(kind, n_seqs, batch, ctx, steps, sec):
@@ -638,7 +646,10 @@ def main():
     release(llm)
     dbg(rank, 'after exit')
     if world == 1 and args.model == "qwen3-0.6b":
-        line["prefill_roofline"] = prefill_roofline()
+        try:
+            line["prefill_roofline"] = prefill_roofline()
+        except Exception as e:            # an extra object: its failure must not cost the contract line
+            line["prefill_roofline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world > 1 and not args.tp and not args.no_tp_block:
         # the replicas above say nothing about the collective design: the same run also measures the
         # tensor-parallel path (BASELINE configs[3]) over all `world` GPUs, with its TP=1 comparison
