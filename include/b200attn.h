@@ -101,6 +101,11 @@ int b200_reshape_and_cache_2d(const void* key, const void* value, void* k_cache,
  * engine/model_runner.py:303-311).
  * workspace: >= b200_paged_decode_attn_workspace_size(...) bytes, 16-byte aligned.
  * num_ctas: 0 = auto (one persistent CTA per SM), otherwise the persistent grid size.
+ * Supported (anything else returns B200_ERR_UNSUPPORTED, and the workspace-size query returns 0):
+ *   head_dim 64 or 128; num_kv_heads 1, 2, 4 or a multiple of 8; GQA group num_heads/num_kv_heads <= 8
+ *   (the group is the M dimension of one m16n8k16 tile; every BASELINE model fits -- the reference's
+ *   native path takes any grouping with num_heads <= 32, attention_torch_native.py:53-58);
+ *   block_size a multiple of 16; batch * ceil(num_kv_heads/8) <= 2048 per launch.
  * ------------------------------------------------------------------------------- */
 size_t b200_paged_decode_attn_workspace_size(int32_t batch, int32_t num_heads,
                                              int32_t num_kv_heads, int32_t head_dim);
