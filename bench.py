@@ -676,8 +676,15 @@ def main():
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
+        # everything is measured and printed: a rank that failed inside the tp block must not turn the
+        # orderly shutdown into a hang (destroy_process_group itself returns in < 1 s, see
+        # profiles/r02_tp_teardown_probe.log)
+        closer = threading.Timer(60.0, lambda: os._exit(0))
+        closer.daemon = True
+        closer.start()
         dist.barrier()
         dist.destroy_process_group()
+        closer.cancel()
 
 
 if __name__ == "__main__":
