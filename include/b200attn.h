@@ -194,6 +194,14 @@ int b200_prefill_varlen_attn(void* out, const void* q, const void* k, const void
  * un-normalised fp32 partials. A smaller (or NULL) workspace is legal: fewer (or no) key splits. */
 int64_t b200_prefill_workspace_size(int32_t head_dim);
 
+/* Tuning / test hook, process-wide: the tcgen05 prefill kernel has two CTA layouts -- 1 query tile of
+ * 128 rows per CTA with two CTAs per SM, or 2 ping-pong tiles per CTA with one CTA per SM -- and picks
+ * per launch (short sequences and head_dim 64 -> 1; long head_dim-128 sequences and key-split launches
+ * -> 2; csrc/prefill_umma.cu::prefill_query_tiles). 1 or 2 forces a layout, 0 restores the choice.
+ * Results are the same up to fp32 summation order across key splits. Not thread-safe against
+ * concurrent b200_prefill_varlen_attn calls. */
+int b200_prefill_set_query_tiles(int32_t query_tiles_per_cta);
+
 /* ---------------------------------------------------------------------------------
  * K8  fused qkv epilogue: split -> per-head RMSNorm(q,k) -> NeoX RoPE(q,k) -> KV scatter.
  * Replaces the op chain models/qwen3.py:79-88 (q_norm/k_norm: layers/layernorm.py:16-25;

@@ -249,6 +249,7 @@ int prefill_umma_launch(void* out, const void* q, const void* k, const void* v, 
                         int bt_stride, int num_blocks, int block_size, float scale, int dtype,
                         void* workspace, int64_t workspace_bytes, int max_seqlen_k,
                         cudaStream_t stream);  // prefill_umma.cu
+void prefill_force_query_tiles(int qt);        // prefill_umma.cu
 // B200_PREFILL_KERNEL=mma_sync forces the kernel in this file (A/B checks); default = prefill_umma.cu.
 static int prefill_kernel_choice() {
   static int v = [] {
@@ -261,6 +262,12 @@ static int prefill_kernel_choice() {
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_prefill_set_query_tiles(int32_t query_tiles_per_cta) {
+  B200_RETURN_IF(query_tiles_per_cta < 0 || query_tiles_per_cta > 2, B200_ERR_BAD_SHAPE);
+  prefill_force_query_tiles(query_tiles_per_cta);
+  return B200_OK;
+}
 
 extern "C" int64_t b200_prefill_workspace_size(int32_t head_dim) {
   // 148 CTAs x 256 rows x (head_dim fp32 of O + m + l): the most a split launch can write

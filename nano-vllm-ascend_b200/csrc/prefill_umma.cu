@@ -53,12 +53,22 @@ struct PrefillUmmaParams {
   float scale_log2;
 };
 
-constexpr int kUBM = 128, kUBN = 128, kUStages = 2, kUThreads = 320;
+constexpr int kUBM = 128, kUBN = 128;
 
-template <typename T, int D>
-__global__ void __launch_bounds__(kUThreads, 1)
+// QT = query tiles per CTA. QT = 2: the layout described above (one CTA per SM, two tiles ping-pong, K/V
+// tiles shared, 2-stage rings). QT = 1: one 128-row tile per CTA, single-stage K/V rings (K(j+1) is loaded
+// under softmax(j) + PV(j), V(j+1) under S(j+1) + softmax(j+1) -- the chain leaves the time), 97 KB of
+// shared memory, 256 TMEM columns, 192 threads -> TWO CTAs per SM: the two chains sharing the tensor pipe
+// are independent CTAs, so one CTA's prologue (barrier init, TMEM alloc, Q load) and epilogue run under
+// the other's main loop and the hardware balances 128-row items.
+template <typename T, int D, int QT>
+__global__ void __launch_bounds__((4 * QT + 2) * 32, 3 - QT)
 prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const PrefillUmmaParams p) {
+  constexpr int kUStages = QT;                  // K/V ring depth
+  constexpr int kTmaWarp = 4 * QT, kMmaWarp = 4 * QT + 1;
+  constexpr uint32_t kTmemCols = QT * 256;      // O[t] at 128 t, S[t] at QT * 128 + 128 t
+  constexpr uint32_t kSBase = QT * 128;
   constexpr int CH = D / 64;                    // 128-byte chunks per head row
   constexpr int QPANEL = kUBM * 128;            // bytes of one Q panel (128 rows)
   constexpr int KPANEL = kUBN * 128;            // bytes of one K / V panel (128 rows)
@@ -67,8 +77,8 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint8_t* sQ = smem;                            // [2][QTILE]
-  uint8_t* sK = sQ + 2 * QTILE;                  // [kUStages][KTILE]
+  uint8_t* sQ = smem;                            // [QT][QTILE]
+  uint8_t* sK = sQ + QT * QTILE;                  // [kUStages][KTILE]
   uint8_t* sV = sK + kUStages * KTILE;           // [kUStages][KTILE]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kUStages * KTILE);
   uint64_t* q_full = bars;                       // [1]
@@ -87,25 +97,25 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int k0 = p.cu_k[seq], Lk = p.cu_k[seq + 1] - k0;
   const int split = (int)blockIdx.x % p.kv_splits;
   const int m_tile = (int)gridDim.x / p.kv_splits - 1 - (int)blockIdx.x / p.kv_splits;   // heavy (late) tiles first
-  const int m0 = m_tile * 2 * kUBM;
+  const int m0 = m_tile * QT * kUBM;
   if (m0 >= Lq) return;                                       // uniform for the whole CTA
   const int kvh = head / p.G;
   const int off = Lk - Lq;
-  int n_tiles[2];
+  int n_tiles[2] = {0, 0};
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
+  for (int t = 0; t < QT; ++t) {
     const int r0 = m0 + t * kUBM;
     const int n_end = r0 < Lq ? min(Lk, r0 + kUBM + off) : 0;
     n_tiles[t] = n_end > 0 ? (n_end + kUBN - 1) / kUBN : 0;
   }
-  const int ntq = (m0 + kUBM < Lq) ? 2 : 1;
+  const int ntq = (QT == 2 && m0 + kUBM < Lq) ? 2 : 1;
   // this CTA's share of the key tiles: [j_lo, j_hi) of the tiles the later query tile needs
   const int nt_all = max(n_tiles[0], n_tiles[1]);
   const int j_lo = (int)((long long)nt_all * split / p.kv_splits);
   const int j_hi = (int)((long long)nt_all * (split + 1) / p.kv_splits);
   const int NT = j_hi - j_lo;                 // loop trip count; tile index = j_lo + j
 #pragma unroll
-  for (int t = 0; t < 2; ++t) n_tiles[t] = max(0, min(n_tiles[t], j_hi) - j_lo);
+  for (int t = 0; t < QT; ++t) n_tiles[t] = max(0, min(n_tiles[t], j_hi) - j_lo);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -124,13 +134,13 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     mbar_fence_init();
   }
-  if (warp == 9) umma::tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // =========================== TMA producer ===========================
     if (lane < 2) {
       const bool is_k = lane == 0;
@@ -177,7 +187,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     // Warp-uniform control flow, loop-invariant descriptor bases + compile-time offsets, one elected
     // lane issues (as prefill_umma.cu).
@@ -191,7 +201,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto issue_s = [&](int t, int j) {
       if (leader) {
         const uint64_t kd = umma::desc_advance(kd0, (j % kUStages) * KTILE);
-        const uint32_t d = tb + 256 + t * 128;
+        const uint32_t d = tb + kSBase + t * 128;
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint64_t ad = umma::desc_advance(qd0, t * QTILE + (ks >> 2) * QPANEL + (ks & 3) * 32);
@@ -207,7 +217,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&k_full[0], 0);
       umma::fence_after_sync();
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+      for (int t = 0; t < QT; ++t)
         if (n_tiles[t] > 0) issue_s(t, 0);
       if (leader) umma::commit(&k_empty[0]);
       __syncwarp();
@@ -220,9 +230,9 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       umma::fence_after_sync();
       const uint64_t vd = umma::desc_advance(vd0, s * KTILE);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < QT; ++t) {
         if (j < n_tiles[t]) {
-          const uint32_t pa = tb + 256 + t * 128;                  // P[t]: 16 keys = 8 packed columns
+          const uint32_t pa = tb + kSBase + t * 128;                  // P[t]: 16 keys = 8 packed columns
 #pragma unroll
           for (int h = 0; h < 2; ++h) {                            // 64 keys at a time, as they are stored
             mbar_wait(&p_full[2 * t + h], j & 1);
@@ -258,7 +268,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int row = (warp & 3) * 32 + lane;          // row inside the 128-row tile == TMEM lane
     const int qrow = m0 + t * kUBM + row;            // row inside the sequence
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t s_addr = tb + lane_base + 256 + t * 128;
+    const uint32_t s_addr = tb + lane_base + kSBase + t * 128;
     const uint32_t o_addr = tb + lane_base + t * 128;
     const float sl2 = p.scale_log2;
     constexpr float kLazy = 8.f;                     // see prefill_umma.cu: lazy rescale threshold (exp2 domain)
@@ -373,7 +383,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 9) umma::tmem_dealloc(tb, 512);
+  if (warp == kMmaWarp) umma::tmem_dealloc(tb, kTmemCols);
 }
 
 // Split-KV merge: one warp per (query row, head); lane = D/32 consecutive columns. Pieces are
@@ -410,22 +420,22 @@ prefill_combine_kernel(T* __restrict__ out, int64_t out_stride, const float* __r
   for (int i = 0; i < V; i += 2) *reinterpret_cast<uint32_t*>(orow + i) = pack2<T>(acc[i] * inv, acc[i + 1] * inv);
 }
 
-template <typename T, int D>
+template <typename T, int D, int QT>
 static int prefill_umma_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                                  const PrefillUmmaParams& p, int num_seqs, int max_seqlen_q, int total_q,
                                  cudaStream_t stream) {
   constexpr int CH = D / 64;
-  constexpr size_t smem = 1024 + 2 * CH * kUBM * 128 + 2 * kUStages * CH * kUBN * 128 + 32 * 8 + 16;
-  auto kern = prefill_umma_kernel<T, D>;
+  constexpr size_t smem = 1024 + QT * CH * kUBM * 128 + 2 * QT * CH * kUBN * 128 + 32 * 8 + 16;
+  auto kern = prefill_umma_kernel<T, D, QT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int m_tiles = (max_seqlen_q + 2 * kUBM - 1) / (2 * kUBM);
+  const int m_tiles = (max_seqlen_q + QT * kUBM - 1) / (QT * kUBM);
   dim3 grid(m_tiles * p.kv_splits, p.H, num_seqs);
-  launch_pdl(kern, grid, dim3(kUThreads), smem, stream, mq, mk, mv, p);
+  launch_pdl(kern, grid, dim3((4 * QT + 2) * 32), smem, stream, mq, mk, mv, p);
   if (p.kv_splits > 1) {
     const int64_t items = (int64_t)total_q * p.H;
     launch_pdl(prefill_combine_kernel<T, D>, dim3((unsigned)((items + 7) / 8)), dim3(256), 0, stream,
@@ -438,16 +448,32 @@ static int prefill_umma_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, c
 // Key splits for a launch: only when the (sequence, head, 256-row) grid would leave more than half of
 // the SMs idle, at least two 128-key tiles per split, at most 8, and only if the workspace holds them.
 int prefill_kv_splits(int num_seqs, int H, int max_seqlen_q, int max_seqlen_k, int total_q, int D,
-                      int64_t workspace_bytes) {
-  const int sms = 148;
-  const int64_t ctas = (int64_t)((max_seqlen_q + 2 * kUBM - 1) / (2 * kUBM)) * H * num_seqs;
-  if (ctas * 2 > sms) return 1;
+                      int64_t workspace_bytes, int qt) {
+  const int slots = 148 * (3 - qt);            // co-resident CTAs: one per SM at QT = 2, two at QT = 1
+  const int64_t ctas = (int64_t)((max_seqlen_q + qt * kUBM - 1) / (qt * kUBM)) * H * num_seqs;
+  if (ctas * 2 > slots) return 1;
   const int key_tiles = (max_seqlen_k + kUBN - 1) / kUBN;
-  int splits = (int)(sms / ctas);
+  int splits = (int)(slots / ctas);
   if (splits > 8) splits = 8;
   if (splits > key_tiles / 2) splits = key_tiles / 2;
   while (splits > 1 && (int64_t)total_q * H * splits * (D + 2) * 4 > workspace_bytes) --splits;
   return splits < 1 ? 1 : splits;
+}
+
+// Query tiles per CTA for a launch (measured r02, B200, TFLOP/s QT = 1 / QT = 2: 16 x 1024 D128 578 / 550;
+// 4 x 4096 D128 894 / 952; 1 x 8192 D64 623 / 566; q 256 against k 8192 D64, key-split 290 / 300):
+// two small CTAs per SM win while prologue / epilogue are a visible share of a CTA (short sequences) and
+// on the exp2-bound D = 64 shapes; one CTA with two ping-pong tiles sharing each K/V tile wins on long
+// D = 128 sequences and when the grid is so small that keys are split across CTAs anyway.
+// b200_prefill_set_query_tiles(1|2) forces one layout (A/B runs, parity tests of both instantiations).
+static int g_forced_query_tiles = 0;
+void prefill_force_query_tiles(int qt) { g_forced_query_tiles = qt; }
+
+int prefill_query_tiles(int num_seqs, int H, int max_seqlen_q, int D) {
+  if (g_forced_query_tiles) return g_forced_query_tiles;
+  const int64_t ctas2 = (int64_t)((max_seqlen_q + 2 * kUBM - 1) / (2 * kUBM)) * H * num_seqs;
+  if (ctas2 * 2 <= 148) return 2;                 // key-split territory (prefill_kv_splits)
+  return (D == 128 && max_seqlen_q >= 2048) ? 2 : 1;
 }
 
 // Entry used by b200_prefill_varlen_attn (prefill_attn.cu). Returns B200_ERR_UNSUPPORTED when the
@@ -470,8 +496,9 @@ int prefill_umma_launch(void* out, const void* q, const void* k, const void* v,
   p.out = out, p.out_stride = out_stride;
   p.H = H, p.G = H / Hkv, p.block_size = block_size, p.bt_stride = bt_stride;
   p.scale_log2 = scale * 1.4426950408889634f;
+  const int qt = prefill_query_tiles(num_seqs, H, max_seqlen_q, D);
   p.kv_splits = (workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
-                    ? prefill_kv_splits(num_seqs, H, max_seqlen_q, max_seqlen_k, total_q, D, workspace_bytes)
+                    ? prefill_kv_splits(num_seqs, H, max_seqlen_q, max_seqlen_k, total_q, D, workspace_bytes, qt)
                     : 1;
   p.part_o = reinterpret_cast<float*>(workspace);
   p.part_ml = p.part_o + (int64_t)total_q * H * p.kv_splits * D;
@@ -495,11 +522,13 @@ int prefill_umma_launch(void* out, const void* q, const void* k, const void* v,
     rc = get_panel_map(v, rows, (int64_t)Hkv * D * 2, Hkv * CH, p.kv_rows_box, cbox, dtype, &mv);
     if (rc != B200_OK) return rc;
   }
+#define B200_PREFILL_DISPATCH(T, DD)                                                                   \
+  (qt == 2 ? prefill_umma_launch_t<T, DD, 2>(mq, mk, mv, p, num_seqs, max_seqlen_q, total_q, stream) \
+           : prefill_umma_launch_t<T, DD, 1>(mq, mk, mv, p, num_seqs, max_seqlen_q, total_q, stream))
   if (dtype == B200_DTYPE_BF16)
-    return D == 128 ? prefill_umma_launch_t<__nv_bfloat16, 128>(mq, mk, mv, p, num_seqs, max_seqlen_q, total_q, stream)
-                    : prefill_umma_launch_t<__nv_bfloat16, 64>(mq, mk, mv, p, num_seqs, max_seqlen_q, total_q, stream);
-  return D == 128 ? prefill_umma_launch_t<__half, 128>(mq, mk, mv, p, num_seqs, max_seqlen_q, total_q, stream)
-                  : prefill_umma_launch_t<__half, 64>(mq, mk, mv, p, num_seqs, max_seqlen_q, total_q, stream);
+    return D == 128 ? B200_PREFILL_DISPATCH(__nv_bfloat16, 128) : B200_PREFILL_DISPATCH(__nv_bfloat16, 64);
+  return D == 128 ? B200_PREFILL_DISPATCH(__half, 128) : B200_PREFILL_DISPATCH(__half, 64);
+#undef B200_PREFILL_DISPATCH
 }
 
 }  // namespace b200

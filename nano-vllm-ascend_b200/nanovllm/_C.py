@@ -47,6 +47,7 @@ PROTOTYPES = {
                                            c_int32, c_int32, c_int32, c_float, c_int32,
                                            c_void_p, c_int64, c_void_p]),
     "b200_prefill_workspace_size": (c_int64, [c_int32]),
+    "b200_prefill_set_query_tiles": (c_int32, [c_int32]),
     "b200_gather_dequant_fp8": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                           c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                           c_float, c_int32, c_void_p]),

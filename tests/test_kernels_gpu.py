@@ -325,7 +325,18 @@ def test_decode_rejects_bad_arguments():
 
 
 # ------------------------------------------------------------------ varlen prefill attention
-def test_prefill_golden(golden_kernels):
+@pytest.fixture(params=[0, 1, 2], ids=["layout_auto", "one_tile_per_cta", "two_tiles_per_cta"])
+def prefill_layout(request):
+    """Both CTA layouts of the tcgen05 prefill kernel (b200_prefill_set_query_tiles) and the per-launch
+    choice between them must pass every prefill parity test."""
+    from nanovllm import _C
+    lib = _C.load()
+    _C.check(lib.b200_prefill_set_query_tiles(request.param), "b200_prefill_set_query_tiles")
+    yield request.param
+    _C.check(lib.b200_prefill_set_query_tiles(0), "b200_prefill_set_query_tiles")
+
+
+def test_prefill_golden(golden_kernels, prefill_layout):
     ops = _ops()
     for tag in ("d64", "d128"):
         g = golden_kernels[f"prefill_{tag}"]
@@ -341,7 +352,7 @@ def test_prefill_golden(golden_kernels):
 
 
 @pytest.mark.parametrize("H,G,D", [(16, 8, 128), (32, 8, 64), (8, 1, 128), (4, 4, 64)])
-def test_prefill_ragged_packed(H, G, D):
+def test_prefill_ragged_packed(H, G, D, prefill_layout):
     ops = _ops()
     lens = [1, 63, 64, 65, 200, 1024, 7]
     g = torch.Generator().manual_seed(H + D)
@@ -363,7 +374,7 @@ def test_prefill_ragged_packed(H, G, D):
 
 
 @pytest.mark.parametrize("bs", [16, 256])
-def test_prefill_paged_prefix_hit(bs):
+def test_prefill_paged_prefix_hit(bs, prefill_layout):
     """Prefix-cache hit form (attention_ori.py:65-70): q shorter than k, K/V read from the
     paged cache through block_tables, bottom-right causal alignment."""
     ops = _ops()
@@ -388,7 +399,7 @@ def test_prefill_paged_prefix_hit(bs):
     (16, 8, 128, 16, [200, 33], [4096, 150]),           # one sequence with fewer key tiles than splits
     (8, 1, 128, 256, [256, 256], [2048, 1999]),         # 32B TP=8 shard shape, reference page size
 ])
-def test_prefill_split_kv(H, G, D, bs, qlens, klens):
+def test_prefill_split_kv(H, G, D, bs, qlens, klens, prefill_layout):
     """Few query rows against many cached keys: the launch splits every (sequence, head, 256 rows)
     along the keys over several CTAs (un-normalised partials in the workspace + merge kernel). Against
     the oracle's fp32 evaluation, and against the same launch with the split disabled."""
