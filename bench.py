@@ -405,7 +405,7 @@ def decode_workload(llm, group, B, ctx, K, W, prompt_seed, rank):
     torch.cuda.synchronize()
     e2e_s = group.max(max(e0.elapsed_time(e1) / 1e3, time.perf_counter() - t0))
     dbg(rank, 'e2e done')
-    graph = runner.graphs[B]
+    graph, launches = runner.decode_graph(B)       # the graph run() replays at this batch / context
     for _ in range(W):
         graph.replay()
     group.barrier()
@@ -420,7 +420,8 @@ def decode_workload(llm, group, B, ctx, K, W, prompt_seed, rank):
     return {"e2e_s": e2e_s, "dev_s": dev_s, "ttfts": ttfts, "prefill_steps": prefill_steps,
             "prefill_step_ms": [round(t, 2) for t in step_ms], "submit_ms": round(submit_ms, 2),
             "h2d_per": (runner.h2d_bytes - h2d0) / K, "d2h_per": (runner.d2h_bytes - d2h0) / K,
-            "launches": runner.launches_per_graph.get(B, 0) * K, "ctx_now": ctx + W + K}
+            "launches": launches * K, "ctx_now": ctx + W + K,
+            "two_micro_batches": runner.use_split(B, int(runner.h_ctx[:B].sum()))}
 
 
 def attention_roofline(runner, group, B, K, tpw, fp8, peak, peak_src):
@@ -435,10 +436,18 @@ def attention_roofline(runner, group, B, K, tpw, fp8, peak, peak_src):
     L = spec.num_layers
     attn_fn = ops.paged_decode_attn_fp8 if fp8 else ops.paged_decode_attn
 
+    # launched the way the step launches it: the runner's grid size, and -- when the step runs as two
+    # micro-batches at this batch / context -- two launches of half the rows each
+    ctas = runner._attn_ctas(B)
+    split = runner._overlap_split(B) if runner.use_split(B, int(runner.h_ctx[:B].sum())) else 0
+    parts = [(0, split), (split, B)] if split else [(0, B)]
+
     def attn_pass():
         for layer in range(L):
-            attn_fn(q, runner.kv_cache[0, layer], runner.kv_cache[1, layer],
-                    runner.d_tables[:B], runner.d_ctx[:B], D ** -0.5, Hkv, out=o, workspace=ws)
+            for lo, hi in parts:
+                attn_fn(q[lo:hi], runner.kv_cache[0, layer], runner.kv_cache[1, layer],
+                        runner.d_tables[lo:hi], runner.d_ctx[lo:hi], D ** -0.5, Hkv, out=o[lo:hi], workspace=ws,
+                        num_ctas=ctas)
     for _ in range(3):
         attn_pass()
     group.barrier()
@@ -449,9 +458,9 @@ def attention_roofline(runner, group, B, K, tpw, fp8, peak, peak_src):
         attn_pass()
     e1.record()
     torch.cuda.synchronize()
-    launch_s = e0.elapsed_time(e1) / 1e3 / (reps * L)
+    launch_s = e0.elapsed_time(e1) / 1e3 / (reps * L * len(parts))
     ctx_sum = int(runner.d_ctx[:B].sum().item())
-    nbytes = ctx_sum * 2 * Hkv * D * runner.kv_cache.dtype.itemsize       # algorithmic bytes / launch
+    nbytes = ctx_sum * 2 * Hkv * D * runner.kv_cache.dtype.itemsize / len(parts)   # algorithmic bytes / launch
     achieved = nbytes / launch_s / 1e9
     traffic = traffic_ctx = None
     tpath = os.path.join(ROOT, "profiles", "decode_attn_traffic.json")
@@ -460,14 +469,15 @@ def attention_roofline(runner, group, B, K, tpw, fp8, peak, peak_src):
             t = json.load(f)
         # the ncu capture was taken at its own context length: scale its bytes/token to this run's
         per_token = t["dram_bytes_per_launch"] / t["context_tokens_per_launch"]
-        traffic, traffic_ctx = per_token * ctx_sum, t["context_tokens_per_launch"] // B
+        traffic, traffic_ctx = per_token * ctx_sum / len(parts), t["context_tokens_per_launch"] // B
     return {"bound": "hbm", "kernel": "paged_decode_fp8_kernel" if fp8 else "paged_decode_kernel",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": None if traffic is None else
             f"ncu dram__bytes_read+write per cached token at ctx {traffic_ctx} (profiles/"
             f"decode_attn_traffic.json) x this run's {ctx_sum} cached tokens per launch",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes,
-            "us_per_launch": launch_s * 1e6, "layers": L}
+            "us_per_launch": launch_s * 1e6, "layers": L, "launches_per_layer": len(parts),
+            "rows_per_launch": B // len(parts), "grid_ctas": ctas or None}
 
 
 def release(llm):
@@ -622,14 +632,16 @@ def main():
     engines = 1 if args.tp else world
     value = engines * B * K / dev_s
     # KV-read roofline of the whole step at the measured peak (what `value` is bounded by)
-    step_kv_bytes = roof["algorithmic_bytes_per_launch"] * roof["layers"]
+    step_kv_bytes = roof["algorithmic_bytes_per_launch"] * roof["layers"] * roof["launches_per_layer"]
     roof["step_kv_roofline_tokens_per_s"] = B / (step_kv_bytes / (peak * 1e9))
     roof["step_frac_of_kv_roofline"] = (B * K / dev_s) / roof["step_kv_roofline_tokens_per_s"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak" if not args.tp else "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, random token ids)",
-        "config": dict(workload_config(args, world), ctx_during_timing=[ctx + W, r["ctx_now"]]),
+        "config": dict(workload_config(args, world), ctx_during_timing=[ctx + W, r["ctx_now"]],
+                       decode_step="two micro-batches on two streams in one CUDA graph" if r["two_micro_batches"]
+                       else "one batch"),
         "e2e": {"value": engines * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": r["h2d_per"],
                 "d2h_bytes_per_step": r["d2h_per"], "ms_per_step": e2e_s / K * 1e3},
         "ttft_p50_ms": ttfts[len(ttfts) // 2], "ttft_max_ms": ttfts[-1], "prefill_steps": r["prefill_steps"],

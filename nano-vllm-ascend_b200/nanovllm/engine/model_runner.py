@@ -117,6 +117,16 @@ class ModelRunner:
         self._allocate_kv_cache()
         self._init_decode_buffers()
         self.graphs: dict[int, torch.cuda.CUDAGraph] = {}
+        self.split_graphs: dict[int, torch.cuda.CUDAGraph] = {}      # two-micro-batch form of the large buckets
+        # bytes one layer's attention reads per cached token, and one layer's weights (split criterion)
+        self._kv_token_bytes = 2 * max(1, self.spec.num_kv_heads // self.shard_world) * self.spec.head_dim * \
+            self.kv_cache.dtype.itemsize
+        self._layer_weight_bytes = sum(p.numel() * p.element_size()
+                                       for p in self.model.model.layers[0].parameters())
+        if self._overlap_split(config.max_num_seqs):
+            # reduced attention grids as CTA pairs per TPC: the SMs left to the other half are whole TPCs
+            from .. import _C
+            _C.check(_C.load().b200_paged_decode_set_tpc_pairing(1), "b200_paged_decode_set_tpc_pairing")
         if not self.enforce_eager:
             self._capture_decode_graphs()
         if self.world_size > 1 and not self.spmd:
@@ -173,6 +183,7 @@ class ModelRunner:
 
     def exit(self):
         self.graphs.clear()
+        self.split_graphs.clear()
         if self.comm is not None:
             from ..comm import set_comm
             torch.cuda.synchronize()
@@ -315,12 +326,15 @@ class ModelRunner:
         self.d_rng = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.d_keys = torch.zeros(B, dtype=torch.int64, device=self.device)     # sharded sampling keys
         self.h2d_bytes = self.d2h_bytes = 0        # decode-step traffic counters (bench.py e2e)
-        self.launches_per_graph: dict[int, int] = {}
+        self.launches_per_graph: dict = {}             # bucket (or (bucket, "split")) -> launches per replay
+        # two-micro-batch decode (_forward_overlapped): second stream + the joined hidden states
+        self._side_stream = torch.cuda.Stream(self.device)
+        self.d_hidden = torch.zeros(B, self.spec.hidden_size, dtype=self.dtype, device=self.device)
 
-    def _stage_decode(self, seqs: list[Sequence], padded: int):
+    def _stage_decode(self, seqs: list[Sequence], padded: int) -> int:
         """Fill the pinned staging buffer for a decode step and upload it with one copy
         (model_runner.py:292-366). Rows >= len(seqs) are padding: token 0, position 0,
-        context_len 0, slot = (last block, 0), table -1."""
+        context_len 0, slot = (last block, 0), table -1. Returns the step's total context tokens."""
         n = len(seqs)
         bs = self.block_size
         self.h_ids[:n] = [s.last_token for s in seqs]
@@ -361,16 +375,86 @@ class ModelRunner:
         nbytes = self._head_bytes + dirty_hi * self.max_blocks * 4
         self._stage_dev[:nbytes].copy_(self._stage_host[:nbytes], non_blocking=True)
         self.h2d_bytes += nbytes
+        return int(lens.sum())
 
-    def _set_decode_context(self, bs: int, real_bs: int):
-        set_context(False, slot_mapping=self.d_slots[:bs], context_lens=self.d_ctx[:bs],
-                    block_tables=self.d_tables[:bs], is_enforce_eager=self.enforce_eager,
-                    real_bs=real_bs, block_size=self.block_size)
+    def _attn_ctas(self, bs: int) -> int:
+        """Persistent grid of the paged decode kernel for a `bs`-row step (Config.decode_attn_ctas)."""
+        n = self.config.decode_attn_ctas
+        if n >= 0:
+            return n
+        if bs < 128 or self.shard_world > 1 or self._kv_token_bytes < 4096:
+            return 0                    # small launches are latency-bound: every SM helps
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        return max(8, int(sms * 0.7 + 4) // 8 * 8)
+
+    def _set_decode_context(self, bs: int, real_bs: int, lo: int = 0, own_gemm: bool = False, ctas: int | None = None):
+        """Publish rows [lo, bs) of the static decode buffers as the step context."""
+        set_context(False, slot_mapping=self.d_slots[lo:bs], context_lens=self.d_ctx[lo:bs],
+                    block_tables=self.d_tables[lo:bs], is_enforce_eager=self.enforce_eager,
+                    real_bs=real_bs, block_size=self.block_size,
+                    decode_attn_ctas=self._attn_ctas(bs) if ctas is None else ctas, own_gemm=own_gemm)
 
     # ------------------------------------------------------------------ the decode step
-    def _decode_step(self, bs: int):
+    def _overlap_split(self, bs: int) -> int:
+        """Rows of the first micro-batch if a `bs`-row decode step MAY run as two micro-batches, else 0:
+        single GPU (the chain has no collective), dense MLPs (a split would stream every expert twice)."""
+        least = self.config.decode_overlap_min_batch
+        if least <= 0 or bs < max(least, 16) or self.shard_world > 1 or self.spec.num_experts > 0:
+            return 0
+        if not self.use_split_at(bs * self.config.max_model_len):
+            return 0                   # not even full-length contexts would reach the threshold
+        return (bs // 2 + 7) // 8 * 8
+
+    def use_split_at(self, kv_tokens: int) -> bool:
+        if self.config.decode_overlap_min_kv_bytes <= 0:       # tests: every eligible step splits
+            return True
+        return kv_tokens * self._kv_token_bytes >= max(self.config.decode_overlap_min_kv_bytes,
+                                                       20 * self._layer_weight_bytes)
+
+    def use_split(self, bs: int, kv_tokens: int) -> bool:
+        """Does a `bs`-row step over `kv_tokens` cached tokens run as two micro-batches? Only when the
+        attention of one half is long enough to cover the other half's chain (which runs ~2.5x slower
+        next to a kernel that saturates HBM: measured ~100 us against ~37 us per layer for Qwen3-0.6B),
+        and the second read of the layer weights is small against the KV stream."""
+        return bool(self._overlap_split(bs)) and self.use_split_at(kv_tokens)
+
+    def decode_graph(self, bs: int, kv_tokens: int | None = None):
+        """(graph, launches of this library per replay) that run() replays for a `bs`-row bucket over
+        `kv_tokens` cached tokens (default: the context lengths staged by the last step)."""
+        if kv_tokens is None:
+            kv_tokens = int(self.h_ctx[:bs].sum())
+        if bs in self.split_graphs and self.use_split(bs, kv_tokens):
+            return self.split_graphs[bs], self.launches_per_graph[(bs, "split")]
+        return self.graphs[bs], self.launches_per_graph[bs]
+
+    def _forward_overlapped(self, bs: int, split: int) -> torch.Tensor:
+        """The layer stack over rows [0, split) on the current stream and over rows [split, bs) on a
+        second stream. Rows of a decode step are independent sequences, so the two halves share nothing
+        but the weights; what the split buys is overlap of two different bottlenecks -- the paged
+        attention of one half streams KV at the HBM roofline while the other half runs its GEMM / norm /
+        RoPE chain, ~8 launches of a few microseconds each that are latency-bound and would otherwise
+        leave HBM idle. Under CUDA-graph capture the second stream forks from and joins
+        the capturing stream, so the step is still ONE graph with two parallel branches. Every kernel is
+        row-wise (GEMMs included), so the result equals the one-batch step up to cuBLAS' choice of
+        algorithm for M = bs / 2."""
+        real_bs = get_context().real_bs
+        own, ctas = self.config.decode_overlap_own_gemm, self._attn_ctas(bs)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        out = self.d_hidden[:bs]
+        side.wait_stream(main)
+        self._set_decode_context(split, real_bs, 0, own, ctas)
+        out[:split].copy_(self.model(self.d_ids[:split], self.d_pos[:split]))
+        with torch.cuda.stream(side):
+            self._set_decode_context(bs, real_bs, split, own, ctas)
+            out[split:].copy_(self.model(self.d_ids[split:bs], self.d_pos[split:bs]))
+        main.wait_stream(side)
+        self._set_decode_context(bs, real_bs)
+        return out
+
+    def _decode_step(self, bs: int, two_halves: bool = False):
         """Forward + logits + sampling for `bs` rows of the static buffers (graph body)."""
-        hidden = self.model(self.d_ids[:bs], self.d_pos[:bs])
+        split = self._overlap_split(bs) if two_halves else 0
+        hidden = self._forward_overlapped(bs, split) if split else self.model(self.d_ids[:bs], self.d_pos[:bs])
         if self.sharded_sampling:
             self.d_rng.add_(1)
             self._sample_sharded(hidden, self.d_temp[:bs], self.d_keys[:bs], self.d_out[:bs])
@@ -398,19 +482,20 @@ class ModelRunner:
 
     @torch.inference_mode()
     def _capture_decode_graphs(self):
+        from .. import ops
         pool = None
         for bs in reversed(self._buckets()):
-            self._set_decode_context(bs, bs)
-            self._decode_step(bs)                      # warm-up (allocator, cuBLAS heuristics)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            from .. import ops
-            before = ops.launch_count()
-            with torch.cuda.graph(graph, pool=pool):
-                self._decode_step(bs)
-            self.launches_per_graph[bs] = ops.launch_count() - before
-            pool = pool or graph.pool()
-            self.graphs[bs] = graph
+            for two_halves in ([False, True] if self._overlap_split(bs) else [False]):
+                self._set_decode_context(bs, bs)
+                self._decode_step(bs, two_halves)      # warm-up (allocator, cuBLAS heuristics)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                before = ops.launch_count()
+                with torch.cuda.graph(graph, pool=pool):
+                    self._decode_step(bs, two_halves)
+                self.launches_per_graph[(bs, "split") if two_halves else bs] = ops.launch_count() - before
+                pool = pool or graph.pool()
+                (self.split_graphs if two_halves else self.graphs)[bs] = graph
         reset_context()
         torch.cuda.synchronize()
         self.kv_cache[:, :, -1].zero_()                # the dummy block soaked up warm-up writes
@@ -443,12 +528,12 @@ class ModelRunner:
             return out.tolist()
         use_graph = not self.enforce_eager and n <= self.config.max_num_seqs
         bs = next(b for b in self._buckets() if b >= n) if use_graph else n
-        self._stage_decode(seqs, bs)
+        kv_tokens = self._stage_decode(seqs, bs)
         if use_graph:
-            self.graphs[bs].replay()
+            self.decode_graph(bs, kv_tokens)[0].replay()
         else:
             self._set_decode_context(bs, n)
-            self._decode_step(bs)
+            self._decode_step(bs, self.use_split(bs, kv_tokens))
             reset_context()
         self.h_out[:n].copy_(self.d_out[:n], non_blocking=True)
         self.d2h_bytes += n * 8

@@ -82,6 +82,7 @@ class Attention(nn.Module):
         if self.fp8_cache:
             return ops.paged_decode_attn_fp8(q, self.k_cache, self.v_cache, context.block_tables,
                                              context.context_lens, self.scale, self.num_kv_heads,
-                                             self.k_scale, self.v_scale)
+                                             self.k_scale, self.v_scale, num_ctas=context.decode_attn_ctas)
         return ops.paged_decode_attn(q, self.k_cache, self.v_cache, context.block_tables,
-                                     context.context_lens, self.scale, self.num_kv_heads)
+                                     context.context_lens, self.scale, self.num_kv_heads,
+                                     num_ctas=context.decode_attn_ctas)

@@ -13,6 +13,9 @@ import torch.nn.functional as F
 from torch import nn
 
 
+from .. import ops
+from ..utils.context import get_context
+
 _TP_OVERRIDE: tuple[int, int] | None = None
 _TP_COLLECTIVES = True
 
@@ -39,6 +42,16 @@ def tp_rank_size() -> tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def matmul(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+    """x @ weight.T (+ bias): cuBLAS, or -- when the step context asks for it (Context.own_gemm, the
+    two-micro-batch decode step) -- the library's single-CTA tcgen05 kernel, which unlike cuBLAS'
+    clustered 2-CTA kernels can run on whatever SMs a resident attention kernel leaves free."""
+    if (bias is None and x.dim() == 2 and get_context().own_gemm and x.is_contiguous()
+            and weight.shape[0] % 128 == 0 and weight.shape[1] % 64 == 0):
+        return ops.linear_umma(x, weight)
+    return F.linear(x, weight, bias)
 
 
 def divide(a: int, b: int) -> int:
@@ -71,7 +84,7 @@ class ReplicatedLinear(LinearBase):
         param.data.copy_(loaded_weight)
 
     def forward(self, x):
-        return F.linear(x, self.weight, self.bias)
+        return matmul(x, self.weight, self.bias)
 
 
 class ColumnParallelLinear(LinearBase):
@@ -86,7 +99,7 @@ class ColumnParallelLinear(LinearBase):
         param.data.copy_(loaded_weight.narrow(self.tp_dim, self.tp_rank * n, n))
 
     def forward(self, x):
-        return F.linear(x, self.weight, self.bias)
+        return matmul(x, self.weight, self.bias)
 
 
 class MergedColumnParallelLinear(ColumnParallelLinear):
@@ -161,7 +174,7 @@ class RowParallelLinear(LinearBase):
                 else:
                     torch.addmm(bias, x, self.weight.t(), out=buf)
                 return buf          # partial sum; RMSNorm(x, residual) completes the all-reduce
-        y = F.linear(x, self.weight, bias)
+        y = matmul(x, self.weight, bias)
         if self.tp_size > 1 and _TP_COLLECTIVES:
             dist.all_reduce(y)
         return y

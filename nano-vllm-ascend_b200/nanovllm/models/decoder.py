@@ -123,6 +123,10 @@ class DecoderMLP(nn.Module):
         self.act_fn = SiluAndMul()
 
     def forward(self, x):
+        w = self.gate_up_proj.weight
+        if (get_context().own_gemm and self.gate_up_proj.bias is None and x.dim() == 2 and x.is_contiguous()
+                and w.shape[0] % 128 == 0 and w.shape[1] % 64 == 0):
+            return self.down_proj(ops.gate_up_silu_umma(x, w))      # gate|up GEMM + SiluAndMul, one launch
         return self.down_proj(self.act_fn(self.gate_up_proj(x)))
 
 

@@ -167,6 +167,40 @@ def test_cuda_graph_decode_equals_eager():
     assert got == want
 
 
+@pytest.mark.parametrize("model", ["tiny-qwen3", "tiny-qwen3-moe"])
+@pytest.mark.parametrize("eager", [True, False])
+@pytest.mark.parametrize("own_gemm", [False, True])
+def test_two_micro_batch_decode_equals_one_batch(model, eager, own_gemm):
+    """Config.decode_overlap_min_batch: the decode step as two micro-batches on two streams (in one CUDA
+    graph when not eager), attention on a reduced grid, must generate the one-batch tokens. 24 ragged
+    sequences finishing at different steps: buckets 32 / 24 / 16 split 16|16, 16|8, 8|8, the last steps
+    fall below the threshold and run as one batch. With cuBLAS GEMMs in both runs the tokens must be
+    identical; with the library's own tcgen05 GEMMs in the split step (different fp32 summation order)
+    a greedy near-tie may flip a sequence: at most 2 of the 24 may differ."""
+    from nanovllm import SamplingParams
+    rnd = random.Random(8)
+    prompts = [[rnd.randint(0, 511) for _ in range(rnd.randint(3, 60))] for _ in range(24)]
+    kw = dict(seed=4, norm_jitter=0.1, enforce_eager=eager, max_num_seqs=32, num_kvcache_blocks=256,
+              max_num_batched_tokens=2048, graph_batch_sizes=(8, 16, 24))
+    sps = [SamplingParams(temperature=1.0, greedy=True, ignore_eos=True, max_tokens=6 + (i * 7) % 23)
+           for i in range(len(prompts))]
+    one = _engine(model, decode_overlap_min_batch=0, **kw)
+    want = [o["token_ids"] for o in one.generate(prompts, sps, use_tqdm=False)]
+    one.exit()
+    two = _engine(model, decode_overlap_min_batch=16, decode_overlap_min_kv_bytes=0, decode_attn_ctas=100,
+                  decode_overlap_own_gemm=own_gemm, **kw)
+    runner = two.model_runner
+    if model.endswith("moe"):                  # sparse MLPs never split (every expert would stream twice)
+        assert runner._overlap_split(32) == 0
+    else:
+        assert runner._overlap_split(32) == 16 and runner._overlap_split(8) == 0 and runner.use_split(32, 1)
+        assert eager or set(runner.split_graphs) == {16, 24, 32}
+    got = [o["token_ids"] for o in two.generate(prompts, sps, use_tqdm=False)]
+    two.exit()
+    differing = sum(a != b for a, b in zip(got, want))
+    assert differing <= (2 if own_gemm else 0), f"{differing} of {len(want)} sequences differ"
+
+
 def test_engine_matches_oracle_on_ragged_batch():
     """Ragged continuous batch (different lengths finish at different steps) vs the CPU oracle
     evaluated sequence by sequence."""
