@@ -10,7 +10,9 @@ fused norms/activation] + cuBLAS GEMMs + sampling).
   e2e        the same K steps through the public API (LLM.step): per step one H2D of the packed
              step metadata from pinned memory and one D2H of the sampled ids, scheduler included
   roofline   the dominant kernel (paged_decode_kernel) timed alone over all 28 layers' caches
-             (28 GiB streamed per pass, far beyond L2), algorithmic KV bytes / event time
+             (28 GiB streamed per pass, far beyond L2), launched the way the step launches it (the
+             runner's grid; two half-batch launches per layer when the step runs as two micro-batches,
+             with the one-launch-per-layer figure beside it), algorithmic KV bytes / event time
   cpu_baseline  the reference's CPU path (oracle port of models/qwen3.py + torch-native
              attention) on the host cores, bounded sample of the same decode step
 
@@ -442,24 +444,33 @@ def attention_roofline(runner, group, B, K, tpw, fp8, peak, peak_src):
     split = runner._overlap_split(B) if runner.use_split(B, int(runner.h_ctx[:B].sum())) else 0
     parts = [(0, split), (split, B)] if split else [(0, B)]
 
-    def attn_pass():
+    def attn_pass(pieces):
         for layer in range(L):
-            for lo, hi in parts:
+            for lo, hi in pieces:
                 attn_fn(q[lo:hi], runner.kv_cache[0, layer], runner.kv_cache[1, layer],
                         runner.d_tables[lo:hi], runner.d_ctx[lo:hi], D ** -0.5, Hkv, out=o[lo:hi], workspace=ws,
                         num_ctas=ctas)
-    for _ in range(3):
-        attn_pass()
-    group.barrier()
+
+    def seconds_per_pass(pieces, reps):
+        for _ in range(3):
+            attn_pass(pieces)
+        group.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            attn_pass(pieces)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / reps
     reps = max(4, min(K, 32))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        attn_pass()
-    e1.record()
-    torch.cuda.synchronize()
-    launch_s = e0.elapsed_time(e1) / 1e3 / (reps * L * len(parts))
+    launch_s = seconds_per_pass(parts, reps) / (L * len(parts))
     ctx_sum = int(runner.d_ctx[:B].sum().item())
+    whole = None
+    if split:      # for comparison: the same rows as ONE launch per layer (what the one-batch graph does)
+        whole_s = seconds_per_pass([(0, B)], max(4, reps // 2)) / L
+        whole_bytes = ctx_sum * 2 * Hkv * D * runner.kv_cache.dtype.itemsize
+        whole = {"rows_per_launch": B, "us_per_launch": whole_s * 1e6, "achieved": whole_bytes / whole_s / 1e9,
+                 "frac": whole_bytes / whole_s / 1e9 / peak}
     nbytes = ctx_sum * 2 * Hkv * D * runner.kv_cache.dtype.itemsize / len(parts)   # algorithmic bytes / launch
     achieved = nbytes / launch_s / 1e9
     traffic = traffic_ctx = None
@@ -477,7 +488,7 @@ def attention_roofline(runner, group, B, K, tpw, fp8, peak, peak_src):
             f"decode_attn_traffic.json) x this run's {ctx_sum} cached tokens per launch",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes,
             "us_per_launch": launch_s * 1e6, "layers": L, "launches_per_layer": len(parts),
-            "rows_per_launch": B // len(parts), "grid_ctas": ctas or None}
+            "rows_per_launch": B // len(parts), "grid_ctas": ctas or None, "one_launch_per_layer": whole}
 
 
 def release(llm):

@@ -118,14 +118,6 @@ int b200_paged_decode_attn(void* out, const void* q, const void* k_cache, const 
                            size_t workspace_bytes, int32_t num_ctas, int32_t dtype,
                            b200_stream_t stream);
 
-/* Process-wide launch option of both paged decode kernels: when on, a grid smaller than the chip
- * (num_ctas < #SMs, even) is launched as thread-block clusters of 2, which places the CTA pairs on the
- * two SMs of one TPC and so leaves WHOLE TPCs idle. That is what lets the runner's two-micro-batch decode
- * step (engine/model_runner.py) run the cuBLAS GEMMs of one half -- 2-CTA tcgen05 kernels that need a
- * free TPC -- underneath the HBM-bound attention of the other half. The kernels themselves do not use
- * any cluster feature; results are unchanged. */
-int b200_paged_decode_set_tpc_pairing(int32_t on);
-
 /* ---------------------------------------------------------------------------------
  * K1/K2 + K6 over an FP8 (e4m3) KV cache -- SURVEY.md 8f row f3. An EXTENSION of the path: the
  * reference keeps its caches in the model dtype (engine/model_runner.py:218-229); nothing in it is

@@ -44,40 +44,20 @@ inline bool pdl_enabled() {
   }();
   return v != 0;
 }
-// cluster_x > 1: the grid is launched as thread-block clusters of cluster_x CTAs along x. The kernels of
-// this library use no cluster feature; a cluster of 2 only makes the hardware place CTA pairs on the two
-// SMs of one TPC, so that a grid smaller than the chip leaves WHOLE TPCs free for concurrently running
-// kernels that need them (cuBLAS' 2-CTA tcgen05 GEMMs; see decode_attn.cu).
 template <typename... KArgs, typename... Args>
-inline void launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                               cudaStream_t stream, int cluster_x, Args&&... args) {
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                       cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  int n = 0;
-  if (pdl_enabled()) {
-    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  if (cluster_x > 1) {
-    attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = (unsigned)cluster_x;
-    attr[n].val.clusterDim.y = 1;
-    attr[n].val.clusterDim.z = 1;
-    ++n;
-  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = n;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                       cudaStream_t stream, Args&&... args) {
-  launch_pdl_cluster(kernel, grid, block, smem, stream, 1, static_cast<Args&&>(args)...);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -30,7 +30,6 @@
 namespace b200 {
 
 constexpr int kStages = 3;
-int g_decode_tpc_pairing = 0;
 
 template <typename T, int D, int HKV_CTA>
 __global__ void __launch_bounds__(kDecodeThreads, 1)
@@ -458,7 +457,7 @@ static int decode_launch_t(const CUtensorMap& mk, const CUtensorMap& mv, const D
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  launch_pdl_cluster(kern, dim3(grid), dim3(kDecodeThreads), smem, stream, decode_cluster_x(grid), mk, mv, p);
+  launch_pdl(kern, dim3(grid), dim3(kDecodeThreads), smem, stream, mk, mv, p);
   if (grid > 1) {
     // large batches: items are cut into 2-3 pieces -> one block per boundary handles all rows;
     // small batches: one item may span every CTA -> one block per (boundary, row)
@@ -484,11 +483,6 @@ static int decode_launch_d(int hkv_cta, const CUtensorMap& mk, const CUtensorMap
 }  // namespace b200
 
 using namespace b200;
-
-extern "C" int b200_paged_decode_set_tpc_pairing(int32_t on) {
-  g_decode_tpc_pairing = on != 0;
-  return B200_OK;
-}
 
 extern "C" size_t b200_paged_decode_attn_workspace_size(int32_t batch, int32_t num_heads,
                                                         int32_t num_kv_heads, int32_t head_dim) {

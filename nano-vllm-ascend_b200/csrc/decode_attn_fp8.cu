@@ -532,8 +532,7 @@ static int decode_fp8_launch_d(int hkv_cta, const CUtensorMap& mk, const CUtenso
     if (e != cudaSuccess) return (int)e;
     attr_set[hkv_cta] = true;
   }
-  launch_pdl_cluster(kern, dim3(grid), dim3(kDecodeThreads), smem, stream, decode_cluster_x(grid), mk, mv, p,
-                     v_scale);
+  launch_pdl(kern, dim3(grid), dim3(kDecodeThreads), smem, stream, mk, mv, p, v_scale);
   if (grid > 1) {
     const int rows = hkv_cta * p.G;
     const dim3 cgrid(grid - 1, items >= 64 ? 1 : rows);

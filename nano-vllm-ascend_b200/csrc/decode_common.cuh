@@ -127,10 +127,4 @@ static inline int num_sms() {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// b200_paged_decode_set_tpc_pairing (decode_attn.cu): launch grids smaller than the chip as CTA pairs
-extern int g_decode_tpc_pairing;
-static inline int decode_cluster_x(int grid) {
-  return (g_decode_tpc_pairing && grid < num_sms() && grid % 2 == 0) ? 2 : 1;
-}
-
 }  // namespace b200

@@ -34,7 +34,6 @@ PROTOTYPES = {
                                          c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64,
                                          c_int64, c_int32, c_int32, c_int32, c_float, c_void_p,
                                          c_size_t, c_int32, c_int32, c_void_p]),
-    "b200_paged_decode_set_tpc_pairing": (c_int32, [c_int32]),
     "b200_reshape_and_cache_fp8": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_int32, c_int32, c_int32, c_int32, c_int64, c_int64,
                                              c_int32, c_int32, c_float, c_float, c_int32, c_void_p]),

@@ -123,10 +123,6 @@ class ModelRunner:
             self.kv_cache.dtype.itemsize
         self._layer_weight_bytes = sum(p.numel() * p.element_size()
                                        for p in self.model.model.layers[0].parameters())
-        if self._overlap_split(config.max_num_seqs):
-            # reduced attention grids as CTA pairs per TPC: the SMs left to the other half are whole TPCs
-            from .. import _C
-            _C.check(_C.load().b200_paged_decode_set_tpc_pairing(1), "b200_paged_decode_set_tpc_pairing")
         if not self.enforce_eager:
             self._capture_decode_graphs()
         if self.world_size > 1 and not self.spmd:
@@ -401,6 +397,8 @@ class ModelRunner:
         least = self.config.decode_overlap_min_batch
         if least <= 0 or bs < max(least, 16) or self.shard_world > 1 or self.spec.num_experts > 0:
             return 0
+        if self.kv_cache.dtype == torch.uint8:
+            return 0                   # e4m3 cache: half the KV bytes per step; the split form is not validated there
         if not self.use_split_at(bs * self.config.max_model_len):
             return 0                   # not even full-length contexts would reach the threshold
         return (bs // 2 + 7) // 8 * 8

@@ -1,5 +1,5 @@
 """Per-kernel timelines (start, duration, stream) of ONE replayed decode step of the config-2 engine for a
-few variants of the step (one batch / two micro-batches, attention grid size, TPC pairing, cuBLAS or the
+few variants of the step (one batch / two micro-batches, attention grid size, cuBLAS or the
 library's own GEMMs in the split step), plus device-timed ms/step of each variant and an eager check of the
 split forward against the one-batch forward. tools/overlap_summary.py turns a trace into the per-kernel
 table and the attention-busy fraction quoted in DESIGN 3.8. Kernel records come from the CUPTI activity stream through
@@ -63,9 +63,8 @@ def timed(fn, reps):
     return t0.elapsed_time(t1) / reps
 
 
-def recapture(split, ctas, pairing, own):
+def recapture(split, ctas, own):
     """Re-capture bucket B with these step options; returns the graph to replay."""
-    lib.b200_paged_decode_set_tpc_pairing(pairing)
     runner.config.decode_overlap_min_batch = 16 if split else 0
     runner.config.decode_overlap_min_kv_bytes = 0            # every eligible step splits
     runner.config.decode_overlap_own_gemm = bool(own)
@@ -91,24 +90,23 @@ with torch.inference_mode():
         emit(kind="eager_check", own_gemm=own, max_abs=float(d.max()), rms=float(d.pow(2).mean().sqrt()),
              ref_rms=float(want.pow(2).mean().sqrt()))
 
-# name, two micro-batches?, attention CTAs (0 = one per SM), TPC pairing, own GEMMs, profile?
+# name, two micro-batches?, attention CTAs (0 = one per SM), own GEMMs in the split step, profile?
 variants = [
-    ("one_batch_c148", 0, 0, 0, 0, True),
-    ("one_batch_c104", 0, 104, 0, 0, False),
-    ("split_cublas_c104_paired", 1, 104, 1, 0, True),
-    ("split_own_c148", 1, 0, 0, 1, False),
-    ("split_own_c120_paired", 1, 120, 1, 1, False),
-    ("split_own_c104", 1, 104, 0, 1, False),
-    ("split_own_c104_paired", 1, 104, 1, 1, True),
-    ("split_own_c88_paired", 1, 88, 1, 1, False),
-    ("one_batch_c148_again", 0, 0, 0, 0, False),
+    ("one_batch_c148", 0, 0, 0, True),
+    ("one_batch_c104", 0, 104, 0, False),
+    ("split_cublas_c104", 1, 104, 0, True),
+    ("split_own_c148", 1, 0, 1, False),
+    ("split_own_c120", 1, 120, 1, False),
+    ("split_own_c104", 1, 104, 1, True),
+    ("split_own_c88", 1, 88, 1, False),
+    ("one_batch_c148_again", 0, 0, 0, False),
 ]
 results = {}
-for name, split, ctas, pairing, own, prof in variants:
+for name, split, ctas, own, prof in variants:
     try:
-        g, launches = recapture(split, ctas, pairing, own)
+        g, launches = recapture(split, ctas, own)
         ms = timed(g.replay, args.reps)
-        results[name] = (ms, (split, ctas, pairing, own))
+        results[name] = (ms, (split, ctas, own))
         emit(kind="step", variant=name, ms_per_step=round(ms, 4), tok_s=round(B / ms * 1e3, 1), launches=launches)
         if prof:
             with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as p:
@@ -136,6 +134,5 @@ for name in dict.fromkeys(["one_batch_c148", best]):
     dt = (time.perf_counter() - t) / 12
     emit(kind="engine_step", variant=name, ms_per_step=round(dt * 1e3, 4), tok_s=round(B / dt, 1),
          ctx=int(runner.h_ctx[:B].max()))
-lib.b200_paged_decode_set_tpc_pairing(0)
 llm.exit()
 print("overlap_timeline done")

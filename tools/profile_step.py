@@ -21,7 +21,7 @@ ap.add_argument("--model", default="qwen3-0.6b")
 args = ap.parse_args()
 
 llm = LLM(args.model, kvcache_block_size=16, max_num_seqs=args.batch, max_model_len=4096,
-          max_num_batched_tokens=16384, seed=0)
+          max_num_batched_tokens=16384, seed=0, graph_batch_sizes=(args.batch,))
 rnd = random.Random(0)
 sp = SamplingParams(temperature=0.6, ignore_eos=True, max_tokens=64)
 for _ in range(args.batch):
