@@ -123,6 +123,7 @@ class ModelRunner:
             self.kv_cache.dtype.itemsize
         self._layer_weight_bytes = sum(p.numel() * p.element_size()
                                        for p in self.model.model.layers[0].parameters())
+        self._num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         if not self.enforce_eager:
             self._capture_decode_graphs()
         if self.world_size > 1 and not self.spmd:
@@ -380,8 +381,7 @@ class ModelRunner:
             return n
         if bs < 128 or self.shard_world > 1 or self._kv_token_bytes < 4096:
             return 0                    # small launches are latency-bound: every SM helps
-        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        return max(8, int(sms * 0.7 + 4) // 8 * 8)
+        return max(8, int(self._num_sms * 0.7 + 4) // 8 * 8)
 
     def _set_decode_context(self, bs: int, real_bs: int, lo: int = 0, own_gemm: bool = False, ctas: int | None = None):
         """Publish rows [lo, bs) of the static decode buffers as the step context."""

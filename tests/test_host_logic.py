@@ -701,3 +701,48 @@ def test_sharded_sampling_key_packing_arithmetic():
     assert ops.decode_sample_keys(ks).tolist() == [7, 151935, 0]
     out = torch.zeros(3, dtype=torch.int64)
     assert ops.decode_sample_keys(ks, out=out) is out and out.tolist() == [7, 151935, 0]
+
+
+def test_decode_step_form_selection():
+    """ModelRunner's host-side choices for a decode step: one batch or two micro-batches,
+    and the attention grid -- pure arithmetic on the step's context lengths, checked on a stub runner."""
+    import types
+    from nanovllm.config import Config
+    from nanovllm.engine.model_runner import ModelRunner
+
+    def stub(**over):
+        cfg = Config("qwen3-0.6b", kvcache_block_size=16, max_num_seqs=256, max_model_len=4096)
+        for k in list(over):
+            if hasattr(cfg, k):
+                setattr(cfg, k, over.pop(k))
+        r = types.SimpleNamespace(
+            config=cfg, shard_world=1, spec=types.SimpleNamespace(num_experts=0),
+            kv_cache=torch.empty(0, dtype=torch.bfloat16), _num_sms=148,
+            _kv_token_bytes=2 * 8 * 128 * 2,                 # Qwen3-0.6B: 4 KB of KV per token and layer
+            _layer_weight_bytes=31_500_000)
+        r.__dict__.update(over)
+        for name in ("_overlap_split", "use_split_at", "use_split", "_attn_ctas"):
+            setattr(r, name, types.MethodType(getattr(ModelRunner, name), r))
+        return r
+
+    r = stub()
+    assert r._overlap_split(256) == 128 and r._overlap_split(224) == 112 and r._overlap_split(130) == 72
+    assert r._overlap_split(96) == 0                                   # below decode_overlap_min_batch
+    assert r.use_split(256, 256 * 1025) and not r.use_split(256, 256 * 900)      # 1.07 GB / 0.94 GB per layer
+    assert r.use_split(128, 128 * 2048) and not r.use_split(128, 128 * 1024)     # the same bytes from fewer rows
+    assert r._attn_ctas(256) == 104 and r._attn_ctas(128) == 104 and r._attn_ctas(96) == 0
+    assert stub(decode_attn_ctas=0)._attn_ctas(256) == 0 and stub(decode_attn_ctas=72)._attn_ctas(8) == 72
+    assert stub(decode_overlap_min_batch=0)._overlap_split(256) == 0
+    assert stub(shard_world=8)._overlap_split(256) == 0 and stub(shard_world=8)._attn_ctas(256) == 0   # TP ranks
+    assert stub(spec=types.SimpleNamespace(num_experts=128))._overlap_split(256) == 0   # experts would stream twice
+    assert stub(kv_cache=torch.empty(0, dtype=torch.uint8))._overlap_split(256) == 0    # e4m3 cache
+    # weight-heavy layers (Qwen3-32B: ~1 GB per layer): no context length makes the second weight read pay
+    assert stub(_layer_weight_bytes=975_000_000)._overlap_split(256) == 0
+    # Llama-3.2-1B shapes: 2 KB of KV per token and layer, 122 MB of weights per layer -> a 2.4 GB threshold
+    # that 256 full-length (4096-token) contexts = 2.1 GB never reach; longer contexts would
+    llama = stub(_kv_token_bytes=2 * 8 * 64 * 2, _layer_weight_bytes=122_000_000)
+    assert llama._overlap_split(256) == 0 and llama._attn_ctas(256) == 0
+    llama.config.max_model_len = 8192
+    assert llama._overlap_split(256) == 128 and not llama.use_split(256, 256 * 4096) and llama.use_split(256, 256 * 5000)
+    # tests force the split with a zero threshold
+    assert stub(decode_overlap_min_kv_bytes=0, decode_overlap_min_batch=16).use_split(16, 1)
