@@ -203,8 +203,8 @@ _prefill_ws: dict = {}
 
 def prefill_workspace(device, head_dim: int) -> torch.Tensor:
     """The split-KV workspace of the prefill kernel (b200_prefill_workspace_size bytes, a few MB),
-    one per device, allocated on first use -- outside CUDA-graph capture; prefill runs eagerly."""
-    key = (device, head_dim)
+    one per device and stream, allocated on first use -- outside CUDA-graph capture; prefill runs eagerly."""
+    key = (device, head_dim, torch.cuda.current_stream(device).cuda_stream)   # concurrent launches must not share it
     ws = _prefill_ws.get(key)
     if ws is None:
         n = int(_C.load().b200_prefill_workspace_size(int(head_dim)))
