@@ -9,7 +9,8 @@
 // bound by shared-memory operand traffic -- measured instruction costs on this part,
 // profiles/r01_umma_probe.log: SS M128 N64 K16 75 cycles, SS N128 107, TS N128 74 -- and measured
 // 537 / 852 / 504 TFLOP/s on the three shapes of tools/kbench.py where this one does 559 / 926 / 602):
-// CTA = one (sequence, head, 256 query rows[, key split]): two 128-row query tiles t = 0, 1 that ping-pong.
+// Two CTA layouts, template parameter QT = 128-row query tiles per CTA, chosen per launch (prefill_query_tiles).
+// QT = 2: CTA = one (sequence, head, 256 query rows[, key split]): two query tiles t = 0, 1 that ping-pong.
 //   warps 0-3 / 4-7   softmax warpgroup of tile t, one thread per query row (= one TMEM lane): reads
 //                     S[t] (128 fp32 columns) with tcgen05.ld, fp32 online softmax in the exp2 domain
 //                     with lazy rescale of O (only when the row max grew by > 2^8), writes P as packed
@@ -23,11 +24,13 @@
 //                                            B = V MN-major straight from its [key][d] rows
 //                     issue order  S0(0) S1(0) | PV0(0) S0(1) PV1(0) S1(1) | PV0(1) S0(2) ...
 //                     so that the tensor pipe works on tile 1-t while warpgroup t is in its softmax.
-// TMEM (512 columns): O[t] at 128 t, S[t] at 256 + 128 t, P[t] aliases S[t] columns [0, 64).
+//   TMEM (512 columns): O[t] at 128 t, S[t] at 256 + 128 t, P[t] aliases S[t] columns [0, 64).
+//   Shared memory: Q 2 x 32 KiB + K 2 x 32 KiB + V 2 x 32 KiB = 192 KiB at D = 128; one CTA per SM.
+// QT = 1: one query tile per CTA: warps 0-3 softmax, warp 4 TMA, warp 5 MMA; single-stage K / V rings; 256
+//   TMEM columns (O at 0, S at 128), 97 KiB of shared memory -> two CTAs per SM (see the kernel's comment).
 // Hazards: S[t](j+1) overwrites the columns PV[t](j) reads P from -- both are tcgen05.mma of the same
 // issuing thread and execute in issue order; softmax(j+1) of tile t starts only after S[t](j+1) has
 // completed, hence after PV[t](j) has.
-// Shared memory: Q 2 x 32 KiB + K 2 x 32 KiB + V 2 x 32 KiB = 192 KiB at D = 128.
 //
 // Split-KV (few, long rows: the prefix-cache-hit form q_len << k_len, BASELINE config 3): when the grid
 // would leave most SMs idle, `kv_splits` CTAs share one (sequence, head, 256 rows), each takes a
@@ -190,7 +193,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     // Warp-uniform control flow, loop-invariant descriptor bases + compile-time offsets, one elected
-    // lane issues (as prefill_umma.cu).
+    // lane issues.
     const uint32_t idesc_s = umma::make_idesc<T>(kUBM, kUBN, 0, 0);   // S = Q K^T, both K-major
     const uint32_t idesc_o = umma::make_idesc<T>(kUBM, D, 0, 1);      // O = P V, P from TMEM, V MN-major
     const uint64_t qd0 = umma::desc_kmajor(smem_u32(sQ));
@@ -271,7 +274,7 @@ prefill_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t s_addr = tb + lane_base + kSBase + t * 128;
     const uint32_t o_addr = tb + lane_base + t * 128;
     const float sl2 = p.scale_log2;
-    constexpr float kLazy = 8.f;                     // see prefill_umma.cu: lazy rescale threshold (exp2 domain)
+    constexpr float kLazy = 8.f;                     // lazy rescale threshold (exp2 domain): O is rescaled only when the max grew by > 2^8
     float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&s_full[t], j & 1);
@@ -445,8 +448,9 @@ static int prefill_umma_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, c
   return finish_launch(p.kv_splits > 1 ? 2 : 1);
 }
 
-// Key splits for a launch: only when the (sequence, head, 256-row) grid would leave more than half of
-// the SMs idle, at least two 128-key tiles per split, at most 8, and only if the workspace holds them.
+// Key splits for a launch: only when the (sequence, head, QT x 128-row) grid would leave more than half of
+// the co-resident CTA slots idle, at least two 128-key tiles per split, at most 8, and only if the
+// workspace holds them.
 int prefill_kv_splits(int num_seqs, int H, int max_seqlen_q, int max_seqlen_k, int total_q, int D,
                       int64_t workspace_bytes, int qt) {
   const int slots = 148 * (3 - qt);            // co-resident CTAs: one per SM at QT = 2, two at QT = 1
