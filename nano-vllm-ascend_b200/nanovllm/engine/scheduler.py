@@ -83,9 +83,15 @@ class Scheduler:
 
     def _schedule_decode(self) -> list[Sequence]:
         batch: list[Sequence] = []
+        block_size = self.block_manager.block_size
         # 2) one decode step for as many running sequences as fit; evict from the back on OOM
         while self.running and len(batch) < self.max_num_seqs:
             seq = self.running.popleft()
+            if seq.num_tokens % block_size > 1:
+                # 14 steps out of 16 at block size 16: the newest token neither opened nor completed a
+                # block, so can_append is trivially true and may_append has nothing to do
+                batch.append(seq)
+                continue
             while not self.block_manager.can_append(seq):
                 if self.running:
                     self.preempt(self.running.pop())
@@ -126,16 +132,18 @@ class Scheduler:
         self.block_manager.deallocate(seq)
 
     def postprocess(self, seqs: list[Sequence], token_ids: list[int]) -> None:
+        eos, max_model_len = self.eos, self.max_model_len
         for seq, token_id in zip(seqs, token_ids):
-            window, seq.prefill_window = seq.prefill_window, None
+            window = seq.prefill_window
             if window is not None:
+                seq.prefill_window = None
                 seq.num_computed_tokens = window[1]
-                if window[1] < len(seq):
+                if window[1] < seq.num_tokens:
                     continue                # a non-final prompt chunk: its sampled token is meaningless
             seq.append_token(token_id)
-            hit_eos = not seq.ignore_eos and token_id == self.eos
-            out_of_room = (seq.num_completion_tokens == seq.max_tokens or
-                           len(seq) == self.max_model_len)
+            n = seq.num_tokens
+            hit_eos = not seq.ignore_eos and token_id == eos
+            out_of_room = n - seq.num_prompt_tokens == seq.max_tokens or n == max_model_len
             if hit_eos or out_of_room:
                 self.free_seq(seq, FinishReason.EOS if hit_eos else FinishReason.LENGTH)
                 self.running.remove(seq)
