@@ -746,3 +746,27 @@ def test_decode_step_form_selection():
     assert llama._overlap_split(256) == 128 and not llama.use_split(256, 256 * 4096) and llama.use_split(256, 256 * 5000)
     # tests force the split with a zero threshold
     assert stub(decode_overlap_min_kv_bytes=0, decode_overlap_min_batch=16).use_split(16, 1)
+
+
+def test_overlap_summary_tool_on_a_synthetic_trace(tmp_path):
+    """tools/overlap_summary.py (the script behind profiles/r02b_timeline_decode_*.txt): attention-resident
+    time is the UNION of the attention kernels' intervals, whatever the streams."""
+    import json
+    import subprocess
+    ev = []
+
+    def k(name, ts, dur, stream):
+        ev.append({"cat": "kernel", "name": name, "ts": ts, "dur": dur, "args": {"stream": stream, "grid": [1, 1, 1]}})
+    k("void b200::paged_decode_kernel<bf16, 128, 8>(...)", 0.0, 100.0, 7)
+    k("void b200::paged_decode_kernel<bf16, 128, 8>(...)", 60.0, 100.0, 9)        # overlaps the first by 40 us
+    k("void b200::moe_umma_gemm_kernel<bf16, false, 6>(...)", 10.0, 20.0, 9)
+    k("nvjet_tst_64x32_64x16_2x2_2cta_v_bz_TNT", 160.0, 40.0, 7)
+    path = tmp_path / "trace.json"
+    path.write_text(json.dumps({"traceEvents": ev + [{"cat": "cpu_op", "name": "x", "ts": 0, "dur": 1}]}))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "overlap_summary.py"), str(path),
+                          "--window", "0", "50"], capture_output=True, text=True, check=True).stdout
+    assert "4 kernels, step span 200.0 us" in out
+    assert "attention resident 160.0 us = 0.800 of the step (sum of its launches 200.0 us)" in out
+    assert "| cuBLAS 64x32_64x16_2x2_2cta | 1 | 40.0 | 40.00 |" in out
+    assert out.count("  stream ") == 2            # the two kernels starting inside [0, 50)
